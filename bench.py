@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the x266 hot path on B200 (contract: see README / DESIGN.md).
+
+Workload (BASELINE.json configs[4]): 7680x4320 frames of 11-bit synthetic
+residuals (32 400 32x32 blocks per frame), forward 2-D DCT32 with shifts 6/11, FRAMES frames resident in
+HBM per GPU.  A "step" is one pass of the DCT over the whole resident batch of this rank.
+
+  value     = blocks/s, device-resident in -> device-resident out, CUDA events, max over ranks
+  e2e       = the same metric through the host-pointer C-ABI call xDct32Batch() with pinned host buffers
+              (H2D + kernel + D2H inside the timed region) on a bounded sample per step
+  roofline  = algorithmic 4096 B/block / kernel time vs the measured HBM copy bandwidth
+  cpu_baseline = the unmodified reference C (oracle/_ref) on this box's host cores, bounded sample
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, all host threads) on the
+same config / metric.  Launch: `python bench.py --gpus N --steps K --warmup W` (N>1 via torchrun).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCKS_PER_FRAME = 32400            # 7680x4320 / 32x32
+SHIFTS = (6, 11)                    # 10-bit video: shift_1st = log2N-1+(bitDepth-8) = 6, shift_2nd = 11
+METRIC = "dct32_blocks_per_s"
+UNIT = "blocks/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_name(frames):
+    return f"config5: 7680x4320 11-bit residuals, DCT32 shifts 6/11, {frames} frames ({frames * BLOCKS_PER_FRAME} blocks) resident per GPU"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(n_blocks, threads, reps=1, data=None):
+    """Times the reference C (oracle/_ref; falls back to our port when it is absent) on n_blocks blocks."""
+    from oracle import Oracle, Ref, have_ref, build
+    build()
+    o = Oracle()
+    x = o.residual(n_blocks * 1024, 266, 1) if data is None else data
+    if have_ref():
+        r = Ref()
+        kind = "reference"
+        fn = lambda: r.dct32(x.reshape(-1, 32, 32), *SHIFTS, threads=threads)      # noqa: E731
+    else:
+        kind = "port"
+        fn = lambda: o.dct(x.reshape(-1, 32, 32), 5, *SHIFTS, threads=threads)     # noqa: E731
+    best = None
+    y = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        y = fn()
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return n_blocks / best, kind, x, y
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = host_threads()
+    sample_frames = args.ref_frames
+    n = sample_frames * BLOCKS_PER_FRAME
+    from oracle import Oracle
+    x = Oracle().residual(n * 1024, 266, 1)
+    for _ in range(args.warmup):
+        cpu_reference_rate(n, threads, data=x)
+    t0 = time.perf_counter()
+    kind = "reference"
+    for _ in range(args.steps):
+        _, kind, _, _ = cpu_reference_rate(n, threads, data=x)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{sample_frames} frames ({n} blocks) of the workload per step, gcc -O2, {threads} pthreads over contiguous ranges"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16 (int32 accumulate)", "data": "synthetic",
+        "config": {"workload": workload_name(args.frames), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="8K frames resident per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=8, help="frames per e2e step (host buffers)")
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of --impl reference")
+    ap.add_argument("--cpu-frames", type=int, default=16, help="frames of the bounded cpu_baseline sample")
+    ap.add_argument("--variant", default="auto", choices=["auto", "bfly", "imma"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the SATD secondary measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import x266_b200 as xb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the x266_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    xb.lib()                                            # fail loudly if the CUDA library is missing
+    xb.set_dct_variant({"auto": xb.DCT_AUTO, "bfly": xb.DCT_BFLY, "imma": xb.DCT_IMMA}[args.variant])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident synthetic batch: this rank's shard (independent blocks, no collective on the path)
+    n_blocks = args.frames * BLOCKS_PER_FRAME
+    g = torch.Generator(device=dev)
+    g.manual_seed(266 + rank)
+    src = (torch.randint(0, 1024, (n_blocks, 32, 32), device=dev, generator=g, dtype=torch.int16)
+           - torch.randint(0, 1024, (n_blocks, 32, 32), device=dev, generator=g, dtype=torch.int16))
+    dst = torch.empty_like(src)
+    stream = torch.cuda.current_stream()
+    sp, dp, st = src.data_ptr(), dst.data_ptr(), stream.cuda_stream
+
+    def step():
+        xb.xDct32BatchDev(sp, dp, n_blocks, SHIFTS[0], SHIFTS[1], st)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = xb.kernel_launches()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record(stream)
+    torch.cuda.synchronize()
+    launches = xb.kernel_launches() - l0
+    clocks = sampler.stop() if sampler else None
+    barrier()
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
+    kernel_ms = max_over_ranks(sum(per_step) / len(per_step))
+    best_ms = max_over_ranks(min(per_step))
+    value = world * n_blocks * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the host-pointer C-ABI call, pinned host buffers, copies inside the timed region
+    e2e_blocks = args.e2e_frames * BLOCKS_PER_FRAME
+    hin = torch.empty((e2e_blocks, 32, 32), dtype=torch.int16, pin_memory=True)
+    hout = torch.empty_like(hin, pin_memory=True)
+    hin.copy_(src[:e2e_blocks].cpu())
+    hin_np, hout_np = hin.numpy(), hout.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        xb.xDct32Batch(hin_np, *SHIFTS, out=hout_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        xb.xDct32Batch(hin_np, *SHIFTS, out=hout_np)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * e2e_blocks * e2e_steps / e2e_s
+    e2e_ok = bool(np.array_equal(hout_np, dst[:e2e_blocks].cpu().numpy()))
+
+    # ---- SATD secondary numbers (same run, rank-local, reported per GPU)
+    secondary = []
+    if not args.no_secondary:
+        peak, peak_src = measured_peaks()
+        n_c = 1 << 24                                                     # 16.8M candidates = 2.1 GB of diffs
+        d = torch.randint(-255, 256, (n_c, 64), device=dev, generator=g, dtype=torch.int16)
+        o = torch.empty(n_c, device=dev, dtype=torch.int32)
+        for _ in range(3):
+            xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), n_c, st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), n_c, st)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = n_c * 132 / (ms * 1e-3) / 1e9
+        secondary.append({"metric": "satd8x8_batch_candidates_per_s_per_gpu", "value": n_c / (ms * 1e-3), "ms_per_launch": ms,
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                       "traffic": None, "algorithmic_bytes_per_candidate": 132}})
+        del d, o
+        # config 3: full search +-32 over one 1920x1080 frame, argmin + full u32 cost surface
+        w, h, rg = 1920, 1080, 32
+        cur = torch.randint(0, 256, (h, w), device=dev, generator=g, dtype=torch.uint8)
+        refp = torch.randint(0, 256, (h + 2 * rg, w + 2 * rg), device=dev, generator=g, dtype=torch.uint8)
+        nb = (w // 8) * (h // 8)
+        cost = torch.empty((nb, 65, 65), device=dev, dtype=torch.int32)
+        best = torch.empty((nb, 3), device=dev, dtype=torch.int32)
+        call = lambda: xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 2 * rg, w, h, rg, 0, nb,   # noqa: E731
+                                            cost.data_ptr(), best.data_ptr(), st)
+        for _ in range(2):
+            call()
+        e0.record(stream)
+        for _ in range(5):
+            call()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        cands = nb * 65 * 65
+        secondary.append({"metric": "satd8x8_search_candidates_per_s_per_gpu", "value": cands / (ms * 1e-3), "ms_per_frame": ms,
+                          "config": "config3: 1920x1080, +-32, u32 cost surface + argmin",
+                          "roofline": {"bound": "int32-alu (not HBM)", "achieved": 551903296 / (ms * 1e-3) / 1e9, "peak": peak,
+                                       "unit": "GB/s", "frac": 551903296 / (ms * 1e-3) / 1e9 / peak, "traffic": None}})
+        del cur, refp, cost, best
+
+    # ---- CPU baseline: the reference C on this box's host cores, bounded sample, rank 0 at N=1 only
+    cpu = None
+    if rank == 0 and world == 1:
+        threads = host_threads()
+        n_cpu = args.cpu_frames * BLOCKS_PER_FRAME
+        xs = src[:n_cpu].cpu().numpy()
+        rate, kind, _, y = cpu_reference_rate(n_cpu, threads, reps=2, data=xs)
+        rate1, _, _, _ = cpu_reference_rate(n_cpu // 8, 1, reps=1, data=xs[: n_cpu // 8])
+        parity = bool(np.array_equal(y.reshape(-1), dst[:n_cpu].cpu().numpy().reshape(-1)))
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{args.cpu_frames} frames ({n_cpu} blocks) of the workload, gcc -O2, best of 2",
+               "single_thread_value": rate1, "gpu_output_bit_exact_on_sample": parity}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = n_blocks * 4096 / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dct32_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16 (s8/u8 byte planes on int8 tensor cores, int32 accumulate)" if args.variant != "bfly" else "int16 (int32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.frames), "variant": args.variant, "l2_policy": "inputs (4.25 GB) larger than L2",
+                       "timing": "CUDA events on the launch stream, max over ranks", "best_ms_per_step": best_ms},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_block": 4096,
+                         "blocks_per_launch": n_blocks, "avg_launch_ms": kernel_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_blocks * 2048, "d2h_bytes_per_step": e2e_blocks * 2048,
+                    "api": "xDct32Batch (host pointers, pinned)", "sample": f"{args.e2e_frames} frames per step per rank",
+                    "matches_device_path": e2e_ok},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

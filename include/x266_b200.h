@@ -1,0 +1,123 @@
+/*
+ * x266_b200.h -- C ABI of libx266_b200.so: the B200 (sm_100a) drop-in for the block-parallel encode
+ * hot path of chenm001/x266 (32x32 integer DCT-II incl. transpose stage, 8x8 Hadamard SATD, 32x32
+ * intra prediction).  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Reference citations are file:line in chenm001/x266 @ 379268c.
+ *
+ * Error convention (src/x266.cpp:494-513): int return, 0 = ok, -1 = failure; xGpuLastError() gives
+ * the text.  There is NO CPU fallback anywhere in this library: with no usable CUDA device every
+ * compute entry point fails (-1, or abort() for the void Tier-1/Tier-2 symbols).
+ */
+#ifndef X266_B200_H
+#define X266_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ================================================================================================
+ * Tier 1 -- the reference's own exported symbols, same names / signatures / semantics.
+ * These are what the Bluesim BDPI runtime binds via `import "BDPI"` (src/mkDct32.bsv:409-411,
+ * src/mkSatd.bsv:204-206) when the testbench is linked against src_tb/ *.c (build/Makefile:67).
+ * State is module-global and not re-entrant, exactly like the reference.
+ * ============================================================================================== */
+
+/* replaces src_tb/dct32.c:30-64 -- same values, same layout */
+#ifndef X266_B200_NO_GT32_DECL
+extern const short g_t32[32][32];
+#endif
+
+/* replaces src_tb/dct32.c:178-202.  Draws 2048 rand() values exactly like the reference
+ * ((rand()&0xFF) - (rand()&0xFF) per sample, row-major), then computes the 2-D transform with
+ * shifts 4 / 11 ON THE GPU instead of the two host partialButterfly32 calls. */
+void dct32_genNew(void);
+/* replaces src_tb/dct32.c:205-220: rows lastDiff, lastDiff+1 as 32 little-endian u32 words. */
+void dct32_getDiff(unsigned int res[/*32*/]);
+/* replaces src_tb/dct32.c:223-246: 4 coefficients, column-major walk, packed into 64 bits. */
+unsigned long long dct32_getDct(void);
+
+/* replaces src_tb/satd.c:124-140 (stimulus as above; cost from the GPU kernel). */
+void satd8x8_genNew(void);
+/* replaces src_tb/satd.c:143-147 */
+void satd8x8_getDiff(unsigned int res[/*4*/]);
+/* replaces src_tb/satd.c:149-152 */
+unsigned int satd8x8_getSatd(void);
+
+/* ================================================================================================
+ * Tier 2 -- the two arithmetic kernels, promoted from `static` to exported, HOST pointers,
+ * synchronous, bit-exact.  These are the names a block loop in src/x266.cpp:537-546 would call.
+ * ============================================================================================== */
+
+/* replaces src_tb/dct32.c:66-170.  One 1-D pass over `line` rows of 32 with transposed store:
+ * dst[k*line + j] = (int16)((sum_n g_t32[k][n]*src[j*32+n] + (1<<(shift-1))) >> shift). */
+void partialButterfly32(const int16_t* src, int16_t* dst, int shift, int line);
+
+/* replaces src_tb/satd.c:31-118 (int16-wrapping 8x8 Hadamard, (sum|.|+2)>>2). */
+int satd8x8(const int16_t diff[64]);
+
+/* ================================================================================================
+ * Tier 3 -- batched entry points in the style of src/x266.cpp (x-prefixed, int 0/-1).
+ * Host-pointer forms copy in/out through an internal chunked, double-buffered stream pipeline
+ * (pinned caller memory is DMA'd directly; pageable memory is staged).  *Dev forms take device
+ * pointers on the current device plus a cudaStream_t passed as void* (NULL = legacy default
+ * stream), enqueue only, and never synchronise.
+ * ============================================================================================== */
+
+/* Mirrors xCodecInit/xCodecFree (src/x266.cpp:494-524).  device < 0 = current device.  Optional:
+ * every entry point initialises lazily on the calling thread's current device. */
+int  xGpuInit(int device);
+void xGpuFree(void);
+const char* xGpuLastError(void);
+/* Number of kernels this library has launched since load (for the bench's gpu_launches claim). */
+unsigned long long xGpuKernelLaunches(void);
+
+/* DCT kernel variants */
+enum {
+    X266_DCT_AUTO  = 0,   /* best measured variant (IMMA) */
+    X266_DCT_BFLY  = 1,   /* CUDA-core partial butterfly, one block per warp, smem transpose */
+    X266_DCT_IMMA  = 2    /* int8 tensor-core (mma.sync m16n8k32) byte-plane dense product   */
+};
+int xGpuSetDctVariant(int variant);
+
+/* 2-D forward 32x32 transform of nBlocks contiguous row-major int16 blocks:
+ * dst = pass(shift2nd) o pass(shift1st), i.e. src_tb/dct32.c:197-198 on every block. */
+int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd);
+int xDct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int shift1st, int shift2nd, void* stream);
+
+/* N x N forward transform, log2N in {2,3,4,5}; matrix rows g_t32[k*32/N][0..N) (dct32.c:109-143),
+ * shifts per src/mkDct32.bsv:93-98. */
+int xDctNBatch(int log2N, const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd);
+int xDctNBatchDev(int log2N, const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int shift1st, int shift2nd, void* stream);
+
+/* one 1-D pass, device pointers (Tier-2 partialButterfly32 on resident data) */
+int xPartialButterfly32Dev(const int16_t* dSrc, int16_t* dDst, int shift, int line, void* stream);
+
+/* SATD of n contiguous 8x8 int16 difference blocks (128 B each) -> n int32 costs. */
+int xSatd8x8Batch(const int16_t* diff, int32_t* satd, size_t n);
+int xSatd8x8BatchDev(const int16_t* dDiff, int32_t* dSatd, size_t n, void* stream);
+
+/* Full search.  cur: w x h u8, stride w (w,h multiples of 8).  refPadded: reference plane
+ * edge-replicated by `range` pixels on every side, stride strd >= w + 2*range.  For the 8x8 blocks
+ * [blk0, blk1) in raster order and every mv in [-range,range]^2:
+ *   cost[(b-blk0)][(mvy+range)][(mvx+range)] = satd8x8(cur_block - ref_block(mv))       (u32)
+ *   best[(b-blk0)][3] = {min cost, mvx, mvy}; ties -> smallest mvx^2+mvy^2, then raster order.
+ * cost and/or best may be NULL. */
+int xSatd8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                   size_t blk0, size_t blk1, uint32_t* cost, int32_t* best);
+int xSatd8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                      size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream);
+
+/* 32x32 intra prediction (src/mkIntra32-wip.bsv:34-48,61-397): n predictions; refs[i] = 64 left
+ * pixels then 65 top pixels (corner first) = 129 bytes; mode[i] in 0..34 (0 planar, 1 DC, 2..34
+ * angular); pred[i] = 32x32 u8 row-major. */
+int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n);
+int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8_t* dPred, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X266_B200_H */

@@ -1,0 +1,253 @@
+"""GPU suite: bit-exact parity of the CUDA path, called through the C ABI, against the oracle, the
+committed reference vectors, the KAT hashes, and (when oracle/_ref travelled) the reference itself."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHIFTS = {2: (1, 8), 3: (2, 9), 4: (3, 10), 5: (4, 11)}
+VARIANTS = ["bfly", "imma"]
+
+
+@pytest.fixture(params=VARIANTS)
+def variant(request, x266):
+    x266.set_dct_variant(x266.DCT_BFLY if request.param == "bfly" else x266.DCT_IMMA)
+    yield request.param
+    x266.set_dct_variant(x266.DCT_AUTO)
+
+
+# ---------------------------------------------------------------------------------------- DCT32
+def test_dct32_reference_vectors(x266, vectors, variant):
+    x = vectors["dct_in"]
+    for key, sh in (("dct_out_4_11", (4, 11)), ("dct_out_6_11", (6, 11)), ("dct_out_1_1", (1, 1)), ("dct_out_9_16", (9, 16))):
+        got = x266.xDct32Batch(x, *sh)
+        assert np.array_equal(got, vectors[key]), (variant, key)
+
+
+@pytest.mark.parametrize("name", ["KAT-A", "KAT-B", "KAT-C"])
+def test_dct32_kat(x266, orc, kat, variant, name):
+    """config 2: one 1080p frame (2040 blocks), memcmp + FNV of the output."""
+    k = kat[name]
+    x = orc.residual(k["blocks"] * 1024, k["seed"], k["kind"])
+    y = x266.xDct32Batch(x, *k["shifts"])
+    assert y[:4].tolist() == k["out_first4"]
+    assert f"{orc.fnv(y):016x}" == k["fnv_out"]
+    assert np.array_equal(y, orc.dct(x.reshape(-1, 32, 32), 5, *k["shifts"], threads=8).ravel())
+
+
+def test_dct32_8k_frame_kat(x266, orc, kat):
+    """config 5 flavour: one 7680x4320 frame, 11-bit residuals, shifts 6/11 -- hash minted from the reference."""
+    k = kat["KAT-8K"]
+    x = orc.residual(k["blocks"] * 1024, k["seed"], k["kind"])
+    for v in (x266.DCT_IMMA, x266.DCT_BFLY):
+        x266.set_dct_variant(v)
+        y = x266.xDct32Batch(x, *k["shifts"])
+        assert f"{orc.fnv(y):016x}" == k["fnv_out"]
+    x266.set_dct_variant(x266.DCT_AUTO)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 8, 9, 63, 295, 296, 297, 2367, 2369, 8192 + 5, 3 * 8192 + 1])
+def test_dct32_ragged_batch_sizes(x266, orc, variant, n):
+    """empty / ragged batches around the warps-per-CTA, resident-grid and pipeline-chunk boundaries."""
+    x = orc.residual(n * 1024, 31 + n, 2)
+    y = x266.xDct32Batch(x, 4, 11)
+    assert y.shape == x.shape
+    if n:
+        assert np.array_equal(y, orc.dct(x.reshape(-1, 32, 32), 5, 4, 11, threads=8).ravel())
+
+
+def test_dct32_extremes_and_wrap(x266, orc, variant):
+    blocks = [np.full(1024, v, np.int16) for v in (0, 1, -1, 255, -255, 1023, -1023, 32767, -32768)]
+    blocks.append(np.where(np.arange(1024) % 2 == 0, 32767, -32768).astype(np.int16))
+    blocks.append(np.where(np.arange(1024) % 2 == 0, -32768, 32767).astype(np.int16))
+    g = orc.g32()
+    for k in (1, 15, 31):            # worst-case sign patterns: maximise |sum| of row k in both passes
+        blocks.append(np.where(np.tile(g[k], 32) >= 0, 32767, -32768).astype(np.int16))
+        blocks.append(np.where(np.repeat(g[k], 32) >= 0, -32768, 32767).astype(np.int16))
+    x = np.stack(blocks).reshape(-1, 32, 32)
+    for sh in ((4, 11), (6, 11), (1, 1), (16, 16), (1, 16)):
+        assert np.array_equal(x266.xDct32Batch(x, *sh), orc.dct(x, 5, *sh)), sh
+    assert int(x266.xDct32Batch(np.full(1024, 1023, np.int16), 4, 11)[0]) == -128
+
+
+def test_dct32_against_live_reference(x266, ref, variant):
+    rng = np.random.default_rng(11)
+    x = rng.integers(-32768, 32768, (4096, 32, 32)).astype(np.int16)
+    assert np.array_equal(x266.xDct32Batch(x, 4, 11), ref.dct32(x, 4, 11, threads=8))
+
+
+def test_dct32_linearity_property_full_size(x266, orc):
+    """size-independent property at the bench size (config 5: 64 frames of 8K = 2.07M blocks is too big
+    for a CPU check): with shifts that cannot round (inputs multiples of 2^15 are not needed -- we use
+    the impulse identity instead): T(e_k) reads back g_t32, and T is exactly additive on inputs whose
+    pass-1 sums are multiples of 2^shift1 and pass-2 sums multiples of 2^shift2."""
+    g = orc.g32().astype(np.int64)
+    # impulse at (r, c) scaled by 2^10: pass 1 gives 2^6 * g[k][c] at coef[k][r]; pass 2 gives
+    # (2^6 * g[k][c] * g[k2][r] + 1024) >> 11 -- closed form, checked for a full frame of impulses
+    n = 32400
+    rr = np.arange(n) % 32
+    cc = (np.arange(n) // 32) % 32
+    x = np.zeros((n, 32, 32), np.int16)
+    x[np.arange(n), rr, cc] = 1024
+    y = x266.xDct32Batch(x, 4, 11).reshape(n, 32, 32)
+    for b in (0, 1, 33, 1023, 5000, n - 1):
+        want = ((64 * np.outer(g[:, rr[b]], g[:, cc[b]]) + 1024) >> 11).astype(np.int16)
+        assert np.array_equal(y[b], want)
+
+
+# ------------------------------------------------------------------------------ Tier 2 / Tier 1
+@pytest.mark.parametrize("line", [1, 5, 32, 33, 1000])
+def test_partialButterfly32_tier2(x266, orc, line):
+    x = orc.residual(line * 32, line, 2)
+    for shift in (1, 4, 11, 16):
+        assert np.array_equal(x266.partialButterfly32(x, shift, line), orc.partial(x, shift, line))
+
+
+def test_partialButterfly32_reference_vector(x266, vectors):
+    assert np.array_equal(x266.partialButterfly32(vectors["partial_src"], 4, 5), vectors["partial_out_shift4_line5"])
+
+
+def test_satd8x8_tier2(x266, orc, vectors):
+    for d, want in zip(vectors["satd_in"][:40], vectors["satd_out"][:40]):
+        assert x266.satd8x8(d) == int(want)
+    assert x266.satd8x8(np.full(64, 1023, np.int16)) == 16
+
+
+def test_bdpi_stream_matches_testbench_vectors(x266, kat, vectors):
+    """Tier 1: srand(1); dct32_genNew/getDiff/getDct and satd8x8_* call for call, as mkTb drives them
+    (src/mkDct32.bsv:430-470, src/mkSatd.bsv:222-252), against the stream the reference produced."""
+    libc = C.CDLL(None)
+    libc.srand(1)
+    diff, words = x266.bdpi_dct_block()
+    assert np.array_equal(diff, vectors["srand1_getDiff"])
+    assert np.array_equal(words, vectors["srand1_getDct"])
+    assert f"{int(words[0]):016x}" == kat["srand1"]["getDct_word0"]
+    libc.srand(1)
+    rows, satd = x266.bdpi_satd_block()
+    assert np.array_equal(rows, vectors["srand1_satd_rows"]) and satd == kat["srand1"]["satd_first"]
+
+
+def test_bdpi_stream_against_live_reference(x266, ref):
+    libc = C.CDLL(None)
+    libc.srand(12345)
+    want = [ref.bdpi_dct_block()[:2] for _ in range(11)]            # the testbench checks 11 blocks
+    libc.srand(12345)
+    for wd, ww in want:
+        gd, gw = x266.bdpi_dct_block()
+        assert np.array_equal(gd, wd) and np.array_equal(gw, ww)
+    libc.srand(777)
+    want = [ref.bdpi_satd_block() for _ in range(256)]              # mkSatd.bsv: 256 iterations
+    libc.srand(777)
+    for wr, ws in want:
+        gr, gs = x266.bdpi_satd_block()
+        assert np.array_equal(gr, wr) and gs == ws
+
+
+# ------------------------------------------------------------------------------------ DCT N<32
+@pytest.mark.parametrize("log2n", [2, 3, 4])
+@pytest.mark.parametrize("nblk", [1, 3, 64, 1000, 4097])
+def test_dctN(x266, orc, log2n, nblk):
+    n = 1 << log2n
+    for kind in (0, 2):
+        x = orc.residual(nblk * n * n, 5 + nblk, kind)
+        s1, s2 = SHIFTS[log2n]
+        got = x266.xDctNBatch(log2n, x, s1, s2)
+        assert np.array_equal(got, orc.dct(x.reshape(-1, n, n), log2n, s1, s2, threads=4).ravel())
+
+
+# ---------------------------------------------------------------------------------------- SATD
+@pytest.mark.parametrize("name", ["KAT-D", "KAT-E"])
+def test_satd_kat(x266, orc, kat, name):
+    k = kat[name]
+    x = orc.residual(k["blocks"] * 64, k["seed"], k["kind"])
+    y = x266.xSatd8x8Batch(x)
+    assert y[:4].tolist() == k["out_first4"]
+    assert f"{orc.fnv(y):016x}" == k["fnv_out"]
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 257, 100003, (1 << 17) + 3])
+def test_satd_ragged(x266, orc, n):
+    x = orc.residual(n * 64, n + 1, 2)
+    y = x266.xSatd8x8Batch(x)
+    assert y.shape == (n,)
+    if n:
+        assert np.array_equal(y, orc.satd(x, threads=8))
+
+
+def test_satd_reference_vectors_and_extremes(x266, vectors):
+    assert np.array_equal(x266.xSatd8x8Batch(vectors["satd_in"]), vectors["satd_out"])
+    assert int(x266.xSatd8x8Batch(np.full(64, 255, np.int16))[0]) == 4080
+    assert int(x266.xSatd8x8Batch(np.full(64, -32768, np.int16))[0]) == int(vectors["satd_out"][66])
+
+
+def make_frames(w, h, rng_px, seed=266):
+    """config 3 synthetic pair: ref = cur shifted by (+5,-3) + small noise, edge-replicated."""
+    r = np.random.default_rng(seed)
+    cur = r.integers(0, 256, (h, w)).astype(np.uint8)
+    ys = np.clip(np.arange(h) + 3, 0, h - 1)
+    xs = np.clip(np.arange(w) - 5, 0, w - 1)
+    ref = np.clip(cur[ys][:, xs].astype(int) + r.integers(-4, 5, (h, w)), 0, 255).astype(np.uint8)
+    return cur, np.pad(ref, rng_px, mode="edge")
+
+
+@pytest.mark.parametrize("rng_px", [0, 3, 8, 32])
+def test_satd_search_small(x266, orc, rng_px):
+    cur, refp = make_frames(64, 48, rng_px)
+    cost, best = x266.xSatd8x8Search(cur, refp, rng_px)
+    wc, wb = orc.satd_search(cur, refp, rng_px, 0, 48)
+    assert np.array_equal(cost, wc)
+    assert np.array_equal(best, wb)
+
+
+def test_satd_search_1080p_sample(x266, orc):
+    """config 3 at full size: whole 1920x1080 frame, +-32; argmins for all 32400 blocks come back in one
+    call; the oracle checks a deterministic sample of 256 full cost surfaces + their argmins, and the
+    interior blocks must find the planted motion (+5,-3)."""
+    cur, refp = make_frames(1920, 1080, 32)
+    nblk = 240 * 135
+    _, best = x266.xSatd8x8Search(cur, refp, 32, want_cost=False)
+    interior = [by * 240 + bx for by in range(8, 127, 17) for bx in range(8, 232, 23)]
+    assert all(best[b, 1] == 5 and best[b, 2] == -3 for b in interior)
+    sample = sorted(set(int(v) for v in np.random.default_rng(1).integers(0, nblk, 256)))
+    for b in sample[:256]:
+        cost, bb = x266.xSatd8x8Search(cur, refp, 32, b, b + 1)
+        wc, wb = orc.satd_search(cur, refp, 32, b, b + 1)
+        assert np.array_equal(cost, wc) and np.array_equal(bb, wb) and np.array_equal(best[b], wb[0])
+
+
+# --------------------------------------------------------------------------------------- intra
+def test_intra32_all_modes(x266, orc):
+    r = np.random.default_rng(5)
+    refs = r.integers(0, 256, (35 * 6, 129)).astype(np.uint8)
+    modes = np.tile(np.arange(35, dtype=np.uint8), 6)
+    refs[0:35] = 0
+    refs[35:70] = 255
+    pred = x266.xIntra32Pred(refs, modes)
+    for i in range(modes.size):
+        assert np.array_equal(pred[i], orc.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))), int(modes[i])
+
+
+# ------------------------------------------------------------------------- device-pointer entry
+def test_device_pointer_entry_points(x266, orc):
+    import torch
+    dev = torch.device("cuda:0")
+    x = orc.residual(1000 * 1024, 9, 1)
+    xs = torch.from_numpy(x).to(dev)
+    ys = torch.empty_like(xs)
+    st = torch.cuda.current_stream().cuda_stream
+    for v in (x266.DCT_BFLY, x266.DCT_IMMA):
+        x266.set_dct_variant(v)
+        ys.zero_()
+        x266.xDct32BatchDev(xs.data_ptr(), ys.data_ptr(), 1000, 6, 11, st)
+        torch.cuda.synchronize()
+        assert np.array_equal(ys.cpu().numpy(), orc.dct(x.reshape(-1, 32, 32), 5, 6, 11, threads=8).ravel())
+    x266.set_dct_variant(x266.DCT_AUTO)
+    d = torch.from_numpy(orc.residual(5000 * 64, 3, 0)).to(dev)
+    o = torch.empty(5000, dtype=torch.int32, device=dev)
+    x266.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), 5000, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(o.cpu().numpy(), orc.satd(d.cpu().numpy()))
+    launches = x266.kernel_launches()
+    assert launches > 0

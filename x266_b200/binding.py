@@ -1,0 +1,210 @@
+"""ctypes binding of libx266_b200.so.  Host-pointer calls take numpy arrays; *Dev calls take raw device
+pointers (ints, e.g. torch.Tensor.data_ptr()) and a stream handle (int, e.g.
+torch.cuda.current_stream().cuda_stream)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libx266_b200.so")
+
+DCT_AUTO, DCT_BFLY, DCT_IMMA = 0, 1, 2
+
+
+class X266Error(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into x266_b200/libx266_b200.so (nvcc cross-compiles
+    without a GPU)."""
+    out = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode:
+        raise X266Error("nvcc build of libx266_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built -- no fallback of any kind."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise X266Error(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the x266_b200 hot path has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    L.xGpuInit.argtypes = [i]
+    L.xGpuLastError.restype = C.c_char_p
+    L.xGpuKernelLaunches.restype = C.c_ulonglong
+    L.xGpuSetDctVariant.argtypes = [i]
+    L.xDct32Batch.argtypes = [vp, vp, sz, i, i]
+    L.xDct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
+    L.xDctNBatch.argtypes = [i, vp, vp, sz, i, i]
+    L.xDctNBatchDev.argtypes = [i, vp, vp, sz, i, i, vp]
+    L.xPartialButterfly32Dev.argtypes = [vp, vp, i, i, vp]
+    L.xSatd8x8Batch.argtypes = [vp, vp, sz]
+    L.xSatd8x8BatchDev.argtypes = [vp, vp, sz, vp]
+    L.xSatd8x8Search.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp]
+    L.xSatd8x8SearchDev.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp]
+    L.xIntra32Pred.argtypes = [vp, vp, vp, sz]
+    L.xIntra32PredDev.argtypes = [vp, vp, vp, sz, vp]
+    L.partialButterfly32.argtypes = [vp, vp, i, i]
+    L.partialButterfly32.restype = None
+    L.satd8x8.argtypes = [vp]
+    L.satd8x8.restype = i
+    L.dct32_getDct.restype = C.c_ulonglong
+    L.satd8x8_getSatd.restype = C.c_uint
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().xGpuLastError().decode()
+
+
+def kernel_launches():
+    return int(lib().xGpuKernelLaunches())
+
+
+def set_dct_variant(v):
+    _ck(lib().xGpuSetDctVariant(v), "xGpuSetDctVariant")
+
+
+def _ck(rc, what):
+    if rc != 0:
+        raise X266Error(f"{what} failed: {last_error()}")
+
+
+def _np(a, dtype):
+    a = np.ascontiguousarray(a, dtype)
+    return a
+
+
+def g_t32():
+    return np.ctypeslib.as_array((C.c_int16 * 1024).in_dll(lib(), "g_t32")).reshape(32, 32).copy()
+
+
+# ---- Tier 2 (reference names) ---------------------------------------------------------------------
+def partialButterfly32(src, shift, line):
+    src = _np(src, np.int16)
+    assert src.size >= line * 32
+    dst = np.zeros(line * 32, np.int16)
+    lib().partialButterfly32(src.ctypes.data, dst.ctypes.data, shift, line)
+    return dst
+
+
+def satd8x8(diff):
+    diff = _np(diff, np.int16)
+    assert diff.size == 64
+    return int(lib().satd8x8(diff.ctypes.data))
+
+
+# ---- Tier 3, host pointers -----------------------------------------------------------------------
+def xDct32Batch(src, shift1st=4, shift2nd=11, out=None):
+    src = _np(src, np.int16)
+    assert src.size % 1024 == 0
+    dst = np.empty_like(src) if out is None else out
+    _ck(lib().xDct32Batch(src.ctypes.data, dst.ctypes.data, src.size // 1024, shift1st, shift2nd), "xDct32Batch")
+    return dst
+
+
+def xDctNBatch(log2n, src, shift1st, shift2nd):
+    src = _np(src, np.int16)
+    bs = 1 << (2 * log2n)
+    assert src.size % bs == 0
+    dst = np.empty_like(src)
+    _ck(lib().xDctNBatch(log2n, src.ctypes.data, dst.ctypes.data, src.size // bs, shift1st, shift2nd), "xDctNBatch")
+    return dst
+
+
+def xSatd8x8Batch(diff):
+    diff = _np(diff, np.int16)
+    assert diff.size % 64 == 0
+    out = np.empty(diff.size // 64, np.int32)
+    _ck(lib().xSatd8x8Batch(diff.ctypes.data, out.ctypes.data, out.size), "xSatd8x8Batch")
+    return out
+
+
+def xSatd8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want_best=True):
+    cur = _np(cur, np.uint8)
+    ref_padded = _np(ref_padded, np.uint8)
+    h, w = cur.shape
+    assert ref_padded.shape == (h + 2 * rng, w + 2 * rng)
+    if blk1 is None:
+        blk1 = (w // 8) * (h // 8)
+    side = 2 * rng + 1
+    nb = blk1 - blk0
+    cost = np.empty((nb, side, side), np.uint32) if want_cost else None
+    best = np.empty((nb, 3), np.int32) if want_best else None
+    _ck(lib().xSatd8x8Search(cur.ctypes.data, ref_padded.ctypes.data, ref_padded.shape[1], w, h, rng, blk0, blk1,
+                             cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None),
+        "xSatd8x8Search")
+    return cost, best
+
+
+def xIntra32Pred(refs, modes):
+    refs = _np(refs, np.uint8).reshape(-1, 129)
+    modes = _np(modes, np.uint8).ravel()
+    assert refs.shape[0] == modes.size
+    pred = np.empty((modes.size, 32, 32), np.uint8)
+    _ck(lib().xIntra32Pred(refs.ctypes.data, modes.ctypes.data, pred.ctypes.data, modes.size), "xIntra32Pred")
+    return pred
+
+
+# ---- Tier 3, device pointers (ints) --------------------------------------------------------------
+def xDct32BatchDev(d_src, d_dst, n_blocks, shift1st, shift2nd, stream=0):
+    _ck(lib().xDct32BatchDev(d_src, d_dst, n_blocks, shift1st, shift2nd, stream), "xDct32BatchDev")
+
+
+def xDctNBatchDev(log2n, d_src, d_dst, n_blocks, shift1st, shift2nd, stream=0):
+    _ck(lib().xDctNBatchDev(log2n, d_src, d_dst, n_blocks, shift1st, shift2nd, stream), "xDctNBatchDev")
+
+
+def xPartialButterfly32Dev(d_src, d_dst, shift, line, stream=0):
+    _ck(lib().xPartialButterfly32Dev(d_src, d_dst, shift, line, stream), "xPartialButterfly32Dev")
+
+
+def xSatd8x8BatchDev(d_diff, d_out, n, stream=0):
+    _ck(lib().xSatd8x8BatchDev(d_diff, d_out, n, stream), "xSatd8x8BatchDev")
+
+
+def xSatd8x8SearchDev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSatd8x8SearchDev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream), "xSatd8x8SearchDev")
+
+
+def xIntra32PredDev(d_refs, d_modes, d_pred, n, stream=0):
+    _ck(lib().xIntra32PredDev(d_refs, d_modes, d_pred, n, stream), "xIntra32PredDev")
+
+
+# ---- Tier 1: drive the BDPI stream the way the Bluesim testbench does -------------------------------
+def bdpi_dct_block():
+    """dct32_genNew(); 16 x dct32_getDiff; 256 x dct32_getDct (src/mkDct32.bsv:430-470)."""
+    L = lib()
+    L.dct32_genNew()
+    buf = (C.c_uint * 32)()
+    diff = []
+    for _ in range(16):
+        L.dct32_getDiff(buf)
+        diff.append(np.array(buf[:], np.uint32))
+    words = np.array([L.dct32_getDct() for _ in range(256)], np.uint64)
+    return np.stack(diff), words
+
+
+def bdpi_satd_block():
+    """satd8x8_genNew(); 8 x satd8x8_getDiff; satd8x8_getSatd (src/mkSatd.bsv:222-252)."""
+    L = lib()
+    L.satd8x8_genNew()
+    buf = (C.c_uint * 4)()
+    rows = []
+    for _ in range(8):
+        L.satd8x8_getDiff(buf)
+        rows.append(np.array(buf[:], np.uint32))
+    return np.stack(rows), int(L.satd8x8_getSatd())

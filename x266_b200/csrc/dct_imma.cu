@@ -1,0 +1,208 @@
+// dct_imma.cu -- 32x32 forward transform on the int8 tensor cores, one transform block per warp,
+// fully register resident between the two passes (no transpose through memory at all).
+//
+// Reference behaviour: src_tb/dct32.c:197-198 (two partialButterfly32 passes, shifts s1/s2).  The
+// dense formulation dst[k][j] = round(sum_n g_t32[k][n]*src[j][n]) is bit-identical to the butterfly
+// because all arithmetic is exact 32-bit integer (|sum| <= 2048*32768 = 2^26).
+//
+// Byte-plane split: an int16 sample x = hi*256 + lo with lo in [0,255] (u8) and hi in [-128,127] (s8),
+// the matrix entries fit s8 (|g| <= 90), so
+//     sum_n g*x = sum_n g*lo  +  256 * sum_n g*hi
+// is two m16n8k32 integer MMAs (s8 x u8 and s8 x s8) with s32 accumulators -- exact.
+//
+// Data flow per block (warp = 32 lanes, g = lane>>2, q = lane&3):
+//   pass 1:  D1[mu][j]  = sum_kappa  A1[mu][kappa] * B1[kappa][j]
+//            A1[mu][kappa] = g_t32[sigma(mu)][pi(kappa)]          (constant fragments, registers)
+//            B1[kappa][j]  = src[j][pi(kappa)]                    (col-major B == row-major src)
+//            -> thread holds coef[sigma(mu)][j] for mu in {16m+8h+g}, j in {8t+2q+e}
+//   pass 2:  D2[k2][nu]  = sum_kappa2 A2[k2][kappa2] * B2[kappa2][nu],  nu = mu (pass-1 row position)
+//            B2[kappa2][nu] = coef[sigma(nu)][pi2(kappa2)]        (taken straight from the pass-1
+//                                                                  accumulator registers)
+//            A2[k2][kappa2] = g_t32[k2][pi2(kappa2)]
+//            -> thread holds dct[k2][sigma(nu)], nu in {8t2+2q+e}: sigma is chosen so that these are
+//               the 8 contiguous columns 8q..8q+7 -> one 128-bit store per output row.
+//   pi, pi2, sigma are pure index permutations; the contraction order is free (exact integers) and
+//   the row order of pass 1 is free, so they cost nothing.
+//
+// Staging: each warp owns a ring of STAGES 2 KiB shared-memory slots filled by the TMA engine with
+// 1-D bulk async copies (cp.async.bulk ... mbarrier::complete_tx), so HBM latency is covered by
+// WARPS*STAGES*2 KiB in flight per CTA independent of register pressure.  Loads from the slot are
+// linear 128-bit (lane*16 + t*512): conflict free.  Stores are 512 contiguous bytes per instruction.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace x266 {
+
+struct G8 { int8_t v[32][32]; };
+constexpr G8 make_g8()
+{
+    G8 g{};
+    for (int k = 0; k < 32; k++)
+        for (int n = 0; n < 32; n++) g.v[k][n] = (int8_t)g32(k, n);
+    return g;
+}
+__constant__ G8 c_g8 = make_g8();
+
+constexpr int IMMA_WARPS = 8;
+constexpr int IMMA_STAGES = 4;
+constexpr int IMMA_SMEM = IMMA_WARPS * IMMA_STAGES * 2048 + IMMA_WARPS * IMMA_STAGES * 8;
+
+__device__ __forceinline__ int perm_sigma(int mu)  { return 8 * ((mu >> 1) & 3) + 2 * (mu >> 3) + (mu & 1); }
+__device__ __forceinline__ int perm_pi(int kappa)  { return 8 * ((kappa & 15) >> 2) + 4 * (kappa >> 4) + (kappa & 3); }
+// kappa2 = 16*hi + 4*q + i  ->  j = 8*(2*hi + (i>>1)) + 2*q + (i&1)
+__device__ __forceinline__ int perm_pi2(int kappa2)
+{
+    const int hi = kappa2 >> 4, q = (kappa2 >> 2) & 3, i = kappa2 & 3;
+    return 8 * (2 * hi + (i >> 1)) + 2 * q + (i & 1);
+}
+
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
+{
+    return (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)(d & 0xFF) << 24);
+}
+
+__global__ void __launch_bounds__(IMMA_WARPS * 32, 2)
+dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const uint32_t ring = smem_u32(smem) + warp * (IMMA_STAGES * 2048);
+    const uint32_t bars = smem_u32(smem) + IMMA_WARPS * IMMA_STAGES * 2048 + warp * (IMMA_STAGES * 8);
+
+    // ---- constant A fragments (m16n8k32 .row layout: a0 (g, 4q+i) a1 (g+8, 4q+i) a2 (g, 16+4q+i) a3 (g+8, 16+4q+i))
+    uint32_t A1[2][4], A2[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int row = 16 * m + g + 8 * (r & 1);
+            const int kb = 16 * (r >> 1) + 4 * q;
+            const int k1 = perm_sigma(row);
+            A1[m][r] = pack4(c_g8.v[k1][perm_pi(kb + 0)], c_g8.v[k1][perm_pi(kb + 1)],
+                             c_g8.v[k1][perm_pi(kb + 2)], c_g8.v[k1][perm_pi(kb + 3)]);
+            A2[m][r] = pack4(c_g8.v[row][perm_pi2(kb + 0)], c_g8.v[row][perm_pi2(kb + 1)],
+                             c_g8.v[row][perm_pi2(kb + 2)], c_g8.v[row][perm_pi2(kb + 3)]);
+        }
+    }
+
+    const size_t first = (size_t)blockIdx.x * IMMA_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * IMMA_WARPS;
+    const uint64_t policy = policy_evict_first();
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < IMMA_STAGES; s++) mbar_init(bars + 8 * s, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+#pragma unroll
+        for (int s = 0; s < IMMA_STAGES; s++) {
+            const size_t b = first + (size_t)s * stride;
+            if (b < nBlocks) {
+                mbar_arrive_expect_tx(bars + 8 * s, 2048);
+                bulk_g2s(ring + s * 2048, src + b * 1024, 2048, bars + 8 * s, policy);
+            }
+        }
+    }
+    __syncwarp();
+
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    const int cAdd1[4] = { add1, add1, add1, add1 };
+    const int cAdd2[4] = { add2, add2, add2, add2 };
+    const int cZero[4] = { 0, 0, 0, 0 };
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (size_t b = first; b < nBlocks; b += stride) {
+        mbar_wait(bars + 8 * stage, parity);
+
+        // ---- B1 fragments: 16-byte chunk q of row j = 8t+g is at slot + t*512 + lane*16 -------
+        uint32_t BL[4][2], BH[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint4 w = ld_shared_v4(ring + stage * 2048 + t * 512 + lane * 16);
+            BL[t][0] = prmt(w.x, w.y, 0x6420); BH[t][0] = prmt(w.x, w.y, 0x7531);
+            BL[t][1] = prmt(w.z, w.w, 0x6420); BH[t][1] = prmt(w.z, w.w, 0x7531);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const size_t nb = b + (size_t)IMMA_STAGES * stride;
+            if (nb < nBlocks) {
+                fence_proxy_async();    // order the generic-proxy reads above before the async-proxy refill
+                mbar_arrive_expect_tx(bars + 8 * stage, 2048);
+                bulk_g2s(ring + stage * 2048, src + nb * 1024, 2048, bars + 8 * stage, policy);
+            }
+        }
+
+        // ---- pass 1 ---------------------------------------------------------------------------
+        uint32_t B2L[4][2], B2H[4][2];
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            int r[4][4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int dl[4], dh[4];
+                mma_s8u8(dl, A1[m], BL[t][0], BL[t][1], cAdd1);
+                mma_s8s8(dh, A1[m], BH[t][0], BH[t][1], cZero);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r[t][c] = (dl[c] + dh[c] * 256) >> shift1;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t p0 = prmt(r[0][2 * h], r[0][2 * h + 1], 0x5140);
+                const uint32_t p1 = prmt(r[1][2 * h], r[1][2 * h + 1], 0x5140);
+                const uint32_t p2 = prmt(r[2][2 * h], r[2][2 * h + 1], 0x5140);
+                const uint32_t p3 = prmt(r[3][2 * h], r[3][2 * h + 1], 0x5140);
+                B2L[2 * m + h][0] = prmt(p0, p1, 0x5410); B2H[2 * m + h][0] = prmt(p0, p1, 0x7632);
+                B2L[2 * m + h][1] = prmt(p2, p3, 0x5410); B2H[2 * m + h][1] = prmt(p2, p3, 0x7632);
+            }
+        }
+
+        // ---- pass 2 + store -------------------------------------------------------------------
+        int16_t* d = dst + b * 1024;
+#pragma unroll
+        for (int m2 = 0; m2 < 2; m2++) {
+            int r[4][4];
+#pragma unroll
+            for (int t2 = 0; t2 < 4; t2++) {
+                int dl[4], dh[4];
+                mma_s8u8(dl, A2[m2], B2L[t2][0], B2L[t2][1], cAdd2);
+                mma_s8s8(dh, A2[m2], B2H[t2][0], B2H[t2][1], cZero);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r[t2][c] = (dl[c] + dh[c] * 256) >> shift2;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint4 o;
+                o.x = prmt(r[0][2 * h], r[0][2 * h + 1], 0x5410);
+                o.y = prmt(r[1][2 * h], r[1][2 * h + 1], 0x5410);
+                o.z = prmt(r[2][2 * h], r[2][2 * h + 1], 0x5410);
+                o.w = prmt(r[3][2 * h], r[3][2 * h + 1], 0x5410);
+                st_global_stream(d + (16 * m2 + 8 * h + g) * 32 + q * 8, o);
+            }
+        }
+
+        if (++stage == IMMA_STAGES) { stage = 0; parity ^= 1; }
+    }
+}
+
+cudaError_t launch_dct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
+{
+    if (nBlocks == 0) return cudaSuccess;
+    static bool attrSet[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attrSet[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(dct32_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IMMA_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attrSet[dev] = true;
+    }
+    size_t want = (nBlocks + IMMA_WARPS - 1) / IMMA_WARPS;
+    size_t cap = (size_t)sm_count() * 2;
+    const int grid = (int)(want < cap ? want : cap);
+    dct32_imma_kernel<<<grid, IMMA_WARPS * 32, IMMA_SMEM, st>>>(src, dst, nBlocks, s1, s2);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace x266

@@ -1,0 +1,22 @@
+// kernels.h -- internal launcher prototypes (C++ side of libx266_b200; not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace x266 {
+
+int sm_count();                 // SMs of the current device (cached per device)
+void count_launch();            // bumps the library-wide kernel launch counter
+
+cudaError_t launch_dct32_bfly(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
+cudaError_t launch_dct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
+cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int line, cudaStream_t st);
+cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
+
+cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st);
+cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                  size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
+cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st);
+
+} // namespace x266

@@ -1,0 +1,229 @@
+// satd.cu -- 8x8 Hadamard SATD: batched cost of precomputed differences, and full-search cost surface.
+//
+// Reference behaviour: src_tb/satd.c:31-118 (satd8x8): rows then columns, 3 butterfly stages each with
+// partner distance 4,2,1 (satd.c:41-66, :73-100), every stage stored to int16 (satd.c:35), cost =
+// (sum |coef| + 2) >> 2 (satd.c:105-113).  Hardware schedule: src/mkSatd.bsv:44-176.
+//
+// int16 wrap: add/sub commute with reduction mod 2^16, so truncating after every stage (reference) is
+// the same as computing in 32 bits and truncating once before the abs -- which is what we do.  The
+// abs itself is taken on the sign-extended value in 32 bits (abs(-32768) = 32768, as in C).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace x266 {
+
+// in-place 8-point Hadamard, partner distances 4,2,1 (the output order is a permutation of the
+// reference's sums-then-differences order; only the multiset matters for sum|.|, and the search
+// kernel uses the same order on both operands).
+template <int STRIDE>
+__device__ __forceinline__ void had8(int* v)
+{
+#pragma unroll
+    for (int dist = 4; dist >= 1; dist >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (!(i & dist)) {
+                const int a = v[i * STRIDE], b = v[(i + dist) * STRIDE];
+                v[i * STRIDE] = a + b;
+                v[(i + dist) * STRIDE] = a - b;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batch: n candidates of 64 int16 (128 B) -> n int32.  One candidate per thread; each warp stages its
+// 32 candidates (4 KiB) with coalesced 128-bit loads into a 128B-XOR-swizzled shared tile so that the
+// per-thread 128-bit row reads are bank-conflict free.
+// ------------------------------------------------------------------------------------------------
+constexpr int SATD_WARPS = 8;
+
+__global__ void __launch_bounds__(SATD_WARPS * 32)
+satd8x8_batch_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
+{
+    __shared__ __align__(128) uint8_t sm[SATD_WARPS][4096];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = smem_u32(&sm[warp][0]);
+    const size_t nGroups = (n + 31) / 32;
+
+    for (size_t grp = (size_t)blockIdx.x * SATD_WARPS + warp; grp < nGroups; grp += (size_t)gridDim.x * SATD_WARPS) {
+        const size_t c0 = grp * 32;
+        const int valid = (int)((n - c0) < 32 ? (n - c0) : 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int gi = i * 32 + lane, cand = gi >> 3, chunk = gi & 7;
+            if (cand < valid)
+                st_shared_v4(base + cand * 128 + ((chunk ^ (cand & 7)) << 4),
+                             ld_global_stream(diff + (c0 + cand) * 64 + chunk * 8));
+        }
+        __syncwarp();
+        if (lane < valid) {
+            int d[64];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const uint4 v = ld_shared_v4(base + lane * 128 + ((r ^ (lane & 7)) << 4));
+                d[8 * r + 0] = (int)(short)(v.x & 0xFFFF); d[8 * r + 1] = (int)v.x >> 16;
+                d[8 * r + 2] = (int)(short)(v.y & 0xFFFF); d[8 * r + 3] = (int)v.y >> 16;
+                d[8 * r + 4] = (int)(short)(v.z & 0xFFFF); d[8 * r + 5] = (int)v.z >> 16;
+                d[8 * r + 6] = (int)(short)(v.w & 0xFFFF); d[8 * r + 7] = (int)v.w >> 16;
+                had8<1>(&d[8 * r]);                       // horizontal
+            }
+            int sad = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                had8<8>(&d[c]);                           // vertical
+#pragma unroll
+                for (int r = 0; r < 8; r++) sad += abs((int)(short)d[8 * r + c]);
+            }
+            out[c0 + lane] = (sad + 2) >> 2;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full search.  One CTA per 8x8 current block; the (8+2R)^2 reference window lives in shared memory.
+// Linearity (exact here: 8-bit pixels give |coef| <= 16320, no int16 wrap is reachable) lets the
+// transform of the current block be computed once, and the vertical half of each reference-window
+// transform be shared by the 8 horizontally overlapping candidates of a row:
+//     T(cur - ref) = T(cur) - H_h( V[my][mx..mx+7] ),   V[my][x] = H_v(window[my..my+7][x]).
+// Per candidate: 8 x (8 LDS + 24 add/sub + 8 sad) instead of the direct 64 sub + 384 + 64 abs + 64 add.
+// ------------------------------------------------------------------------------------------------
+constexpr int SRCH_WARPS = 8;
+
+__global__ void __launch_bounds__(SRCH_WARPS * 32)
+satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd,
+                      int w, int range, size_t blk0, uint32_t* __restrict__ cost, int32_t* __restrict__ best)
+{
+    extern __shared__ __align__(16) uint8_t dynsm[];
+    const int side = 2 * range + 1;
+    const int ws = 2 * range + 8;                  // window width/height (multiple of 4 when range even; padded below)
+    const int wsp = (ws + 3) & ~3;
+    int* tcur = reinterpret_cast<int*>(dynsm);                         // [64] transform of the current block
+    int* tmp = tcur + 64;                                              // [64]
+    int* vAll = tmp + 64;                                              // [SRCH_WARPS][8][wsp]
+    uint8_t* win = reinterpret_cast<uint8_t*>(vAll + SRCH_WARPS * 8 * wsp);   // [ws][wsp]
+    __shared__ unsigned long long sBest[SRCH_WARPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t blk = blk0 + blockIdx.x;
+    const int bw = w >> 3;
+    const int bx = (int)(blk % bw) * 8, by = (int)(blk / bw) * 8;
+
+    // window origin: unpadded pixel (bx-R, by-R) == padded (bx, by)
+    const uint8_t* wsrc = refPad + (intptr_t)by * strd + bx;
+    for (int i = tid; i < ws * ws; i += SRCH_WARPS * 32) {
+        const int yy = i / ws, xx = i - yy * ws;
+        win[yy * wsp + xx] = wsrc[(intptr_t)yy * strd + xx];
+    }
+    if (tid < 8) {                                  // horizontal transform of current row tid
+        int v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[c] = cur[(size_t)(by + tid) * w + bx + c];
+        had8<1>(v);
+#pragma unroll
+        for (int c = 0; c < 8; c++) tmp[tid * 8 + c] = v[c];
+    }
+    __syncthreads();
+    if (tid < 8) {                                  // vertical transform of column tid
+        int v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = tmp[r * 8 + tid];
+        had8<1>(v);
+#pragma unroll
+        for (int r = 0; r < 8; r++) tcur[r * 8 + tid] = v[r];
+    }
+    __syncthreads();
+    int tc[64];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int4 t = reinterpret_cast<const int4*>(tcur)[i];
+        tc[4 * i + 0] = t.x; tc[4 * i + 1] = t.y; tc[4 * i + 2] = t.z; tc[4 * i + 3] = t.w;
+    }
+
+    int* V = vAll + warp * 8 * wsp;
+    unsigned long long bestKey = ~0ull;
+    uint32_t* costBlk = cost ? cost + (size_t)blockIdx.x * side * side : nullptr;
+
+    for (int my = warp; my < side; my += SRCH_WARPS) {
+        // vertical transforms of the 8-row band starting at window row my
+        for (int x = lane; x < ws; x += 32) {
+            int v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = win[(my + i) * wsp + x];
+            had8<1>(v);
+#pragma unroll
+            for (int r = 0; r < 8; r++) V[r * wsp + x] = v[r];
+        }
+        __syncwarp();
+        for (int mx = lane; mx < side; mx += 32) {
+            unsigned sad = 0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                int v[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) v[c] = V[r * wsp + mx + c];
+                had8<1>(v);
+#pragma unroll
+                for (int c = 0; c < 8; c++) sad = __sad(v[c], tc[r * 8 + c], sad);
+            }
+            const unsigned c4 = (sad + 2) >> 2;
+            if (costBlk) costBlk[my * side + mx] = c4;
+            const int dx = mx - range, dy = my - range;
+            const unsigned long long key = ((unsigned long long)c4 << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
+                                           ((unsigned long long)my << 12) | (unsigned long long)mx;
+            bestKey = key < bestKey ? key : bestKey;
+        }
+        __syncwarp();
+    }
+
+    if (best) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, bestKey, o);
+            bestKey = other < bestKey ? other : bestKey;
+        }
+        if (lane == 0) sBest[warp] = bestKey;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long k = sBest[0];
+#pragma unroll
+            for (int i = 1; i < SRCH_WARPS; i++) k = sBest[i] < k ? sBest[i] : k;
+            int32_t* o = best + (size_t)blockIdx.x * 3;
+            o[0] = (int32_t)(k >> 40);
+            o[1] = (int)(k & 0xFFF) - range;
+            o[2] = (int)((k >> 12) & 0xFFF) - range;
+        }
+    }
+}
+
+cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    size_t want = (n + SATD_WARPS * 32 - 1) / (SATD_WARPS * 32);
+    size_t cap = (size_t)sm_count() * 4;
+    satd8x8_batch_kernel<<<(int)(want < cap ? want : cap), SATD_WARPS * 32, 0, st>>>(diff, out, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                  size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
+{
+    if (blk1 <= blk0) return cudaSuccess;
+    if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
+    const int ws = 2 * range + 8, wsp = (ws + 3) & ~3;
+    const size_t smem = 128 * sizeof(int) + (size_t)SRCH_WARPS * 8 * wsp * sizeof(int) + (size_t)ws * wsp;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(satd8x8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const size_t nb = blk1 - blk0;
+    // grid.x is limited to 2^31-1; frames are far below that
+    satd8x8_search_kernel<<<(unsigned)nb, SRCH_WARPS * 32, smem, st>>>(cur, refPad, strd, w, range, blk0, cost, best);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace x266
