@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Small driver for ncu: a few launches of each kernel on resident data (used by scripts/gpu_profile.sh)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import x266_b200 as xb
+
+dev = torch.device("cuda:0")
+torch.cuda.set_device(0)
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+n = frames * 32400
+src = (torch.randint(0, 1024, (n, 32, 32), device=dev, dtype=torch.int16) - torch.randint(0, 1024, (n, 32, 32), device=dev, dtype=torch.int16))
+dst = torch.empty_like(src)
+st = torch.cuda.current_stream().cuda_stream
+for v in (xb.DCT_IMMA, xb.DCT_BFLY):
+    xb.set_dct_variant(v)
+    for _ in range(3):
+        xb.xDct32BatchDev(src.data_ptr(), dst.data_ptr(), n, 6, 11, st)
+nc = 1 << 22
+d = torch.randint(-255, 256, (nc, 64), device=dev, dtype=torch.int16)
+o = torch.empty(nc, device=dev, dtype=torch.int32)
+for _ in range(3):
+    xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), nc, st)
+w, h, rg = 1920, 1080, 32
+cur = torch.randint(0, 256, (h, w), device=dev, dtype=torch.uint8)
+refp = torch.randint(0, 256, (h + 64, w + 64), device=dev, dtype=torch.uint8)
+nb = 240 * 135
+cost = torch.empty((nb, 65, 65), device=dev, dtype=torch.int32)
+best = torch.empty((nb, 3), device=dev, dtype=torch.int32)
+for _ in range(2):
+    xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+torch.cuda.synchronize()
+print("profile driver done")
