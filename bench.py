@@ -55,7 +55,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
@@ -196,7 +196,9 @@ def main():
         return float(t.item())
 
     # ---- resident synthetic batch: this rank's shard (independent blocks, no collective on the path)
-    n_blocks = args.frames * BLOCKS_PER_FRAME
+    from x266_b200.shard import shard_range
+    lo, hi = shard_range(world * args.frames * BLOCKS_PER_FRAME, rank, world)      # weak scaling: global batch grows with N
+    n_blocks = hi - lo
     g = torch.Generator(device=dev)
     g.manual_seed(266 + rank)
     src = (torch.randint(0, 1024, (n_blocks, 32, 32), device=dev, generator=g, dtype=torch.int16)
@@ -208,10 +210,10 @@ def main():
     def step():
         xb.xDct32BatchDev(sp, dp, n_blocks, SHIFTS[0], SHIFTS[1], st)
 
+    sampler = ClockSampler(local) if rank == 0 else None      # sampled across warm-up + timed region (the region itself is tens of ms)
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = xb.kernel_launches()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record(stream)

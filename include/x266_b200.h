@@ -82,6 +82,9 @@ enum {
     X266_DCT_IMMA  = 2    /* int8 tensor-core (mma.sync m16n8k32) byte-plane dense product   */
 };
 int xGpuSetDctVariant(int variant);
+/* Diagnostic/tuning hook (not part of the reference-facing surface): key 0 selects the IMMA kernel's
+ * (warps, stages, CTAs/SM, staging) instantiation used by scripts/tune_dct.py; -1 = shipped default. */
+int xGpuTune(int key, int value);
 
 /* 2-D forward 32x32 transform of nBlocks contiguous row-major int16 blocks:
  * dst = pass(shift2nd) o pass(shift1st), i.e. src_tb/dct32.c:197-198 on every block. */

@@ -45,6 +45,7 @@ def lib():
     L.xGpuLastError.restype = C.c_char_p
     L.xGpuKernelLaunches.restype = C.c_ulonglong
     L.xGpuSetDctVariant.argtypes = [i]
+    L.xGpuTune.argtypes = [i, i]
     L.xDct32Batch.argtypes = [vp, vp, sz, i, i]
     L.xDct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
     L.xDctNBatch.argtypes = [i, vp, vp, sz, i, i]
@@ -76,6 +77,10 @@ def kernel_launches():
 
 def set_dct_variant(v):
     _ck(lib().xGpuSetDctVariant(v), "xGpuSetDctVariant")
+
+
+def tune(key, value):
+    _ck(lib().xGpuTune(key, value), "xGpuTune")
 
 
 def _ck(rc, what):

@@ -43,9 +43,6 @@ constexpr G8 make_g8()
 }
 __constant__ G8 c_g8 = make_g8();
 
-constexpr int IMMA_WARPS = 8;
-constexpr int IMMA_STAGES = 4;
-constexpr int IMMA_SMEM = IMMA_WARPS * IMMA_STAGES * 2048 + IMMA_WARPS * IMMA_STAGES * 8;
 
 __device__ __forceinline__ int perm_sigma(int mu)  { return 8 * ((mu >> 1) & 3) + 2 * (mu >> 3) + (mu & 1); }
 __device__ __forceinline__ int perm_pi(int kappa)  { return 8 * ((kappa & 15) >> 2) + 4 * (kappa >> 4) + (kappa & 3); }
@@ -61,7 +58,10 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
     return (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)(d & 0xFF) << 24);
 }
 
-__global__ void __launch_bounds__(IMMA_WARPS * 32, 2)
+// DIRECT = true replaces the shared-memory ring by register double-buffering with 128-bit global loads
+// (kept as a measured alternative; see DESIGN.md for the sweep).
+template <int IMMA_WARPS, int IMMA_STAGES, int MIN_CTAS, bool DIRECT>
+__global__ void __launch_bounds__(IMMA_WARPS * 32, MIN_CTAS)
 dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -88,23 +88,32 @@ dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, si
 
     const size_t first = (size_t)blockIdx.x * IMMA_WARPS + warp;
     const size_t stride = (size_t)gridDim.x * IMMA_WARPS;
-    const uint64_t policy = policy_evict_first();
+    uint64_t policy = 0;
+    uint4 nxt[4] = {};
 
-    if (lane == 0) {
+    if constexpr (!DIRECT) {
+        policy = policy_evict_first();
+        if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < IMMA_STAGES; s++) mbar_init(bars + 8 * s, 1);
-        fence_mbar_init();
-        fence_proxy_async();
+            for (int s = 0; s < IMMA_STAGES; s++) mbar_init(bars + 8 * s, 1);
+            fence_mbar_init();
+            fence_proxy_async();
 #pragma unroll
-        for (int s = 0; s < IMMA_STAGES; s++) {
-            const size_t b = first + (size_t)s * stride;
-            if (b < nBlocks) {
-                mbar_arrive_expect_tx(bars + 8 * s, 2048);
-                bulk_g2s(ring + s * 2048, src + b * 1024, 2048, bars + 8 * s, policy);
+            for (int s = 0; s < IMMA_STAGES; s++) {
+                const size_t b = first + (size_t)s * stride;
+                if (b < nBlocks) {
+                    mbar_arrive_expect_tx(bars + 8 * s, 2048);
+                    bulk_g2s(ring + s * 2048, src + b * 1024, 2048, bars + 8 * s, policy);
+                }
             }
         }
+        __syncwarp();
+    } else {
+        if (first < nBlocks) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) nxt[t] = ld_global_stream(src + first * 1024 + t * 256 + lane * 8);
+        }
     }
-    __syncwarp();
 
     const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
     const int cAdd1[4] = { add1, add1, add1, add1 };
@@ -114,23 +123,36 @@ dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, si
     int stage = 0;
     uint32_t parity = 0;
     for (size_t b = first; b < nBlocks; b += stride) {
-        mbar_wait(bars + 8 * stage, parity);
-
-        // ---- B1 fragments: 16-byte chunk q of row j = 8t+g is at slot + t*512 + lane*16 -------
+        // ---- B1 fragments: 16-byte chunk q of row j = 8t+g sits at byte t*512 + lane*16 of the block
         uint32_t BL[4][2], BH[4][2];
+        if constexpr (!DIRECT) {
+            mbar_wait(bars + 8 * stage, parity);
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const uint4 w = ld_shared_v4(ring + stage * 2048 + t * 512 + lane * 16);
-            BL[t][0] = prmt(w.x, w.y, 0x6420); BH[t][0] = prmt(w.x, w.y, 0x7531);
-            BL[t][1] = prmt(w.z, w.w, 0x6420); BH[t][1] = prmt(w.z, w.w, 0x7531);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const size_t nb = b + (size_t)IMMA_STAGES * stride;
+            for (int t = 0; t < 4; t++) {
+                const uint4 w = ld_shared_v4(ring + stage * 2048 + t * 512 + lane * 16);
+                BL[t][0] = prmt(w.x, w.y, 0x6420); BH[t][0] = prmt(w.x, w.y, 0x7531);
+                BL[t][1] = prmt(w.z, w.w, 0x6420); BH[t][1] = prmt(w.z, w.w, 0x7531);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const size_t nb = b + (size_t)IMMA_STAGES * stride;
+                if (nb < nBlocks) {
+                    fence_proxy_async();    // order the generic-proxy reads above before the async-proxy refill
+                    mbar_arrive_expect_tx(bars + 8 * stage, 2048);
+                    bulk_g2s(ring + stage * 2048, src + nb * 1024, 2048, bars + 8 * stage, policy);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const uint4 w = nxt[t];
+                BL[t][0] = prmt(w.x, w.y, 0x6420); BH[t][0] = prmt(w.x, w.y, 0x7531);
+                BL[t][1] = prmt(w.z, w.w, 0x6420); BH[t][1] = prmt(w.z, w.w, 0x7531);
+            }
+            const size_t nb = b + stride;
             if (nb < nBlocks) {
-                fence_proxy_async();    // order the generic-proxy reads above before the async-proxy refill
-                mbar_arrive_expect_tx(bars + 8 * stage, 2048);
-                bulk_g2s(ring + stage * 2048, src + nb * 1024, 2048, bars + 8 * stage, policy);
+#pragma unroll
+                for (int t = 0; t < 4; t++) nxt[t] = ld_global_stream(src + nb * 1024 + t * 256 + lane * 8);
             }
         }
 
@@ -182,27 +204,56 @@ dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, si
             }
         }
 
-        if (++stage == IMMA_STAGES) { stage = 0; parity ^= 1; }
+        if constexpr (!DIRECT) {
+            if (++stage == IMMA_STAGES) { stage = 0; parity ^= 1; }
+        }
     }
+}
+
+// ---- configuration table (index = tuning id).  Shipped default = 6 (8 warps, 2 CTAs/SM, register
+// double-buffered 128-bit global loads): 95.7 % of the measured HBM roofline on B200 vs 86.7 % for the
+// best TMA-ring instantiation (profiles/r01_tune_dct.log).
+constexpr int IMMA_DEFAULT_CFG = 6;
+static int g_immaCfg = IMMA_DEFAULT_CFG;
+void set_imma_config(int id) { g_immaCfg = id < 0 ? IMMA_DEFAULT_CFG : id; }
+
+template <int W, int S, int B, bool D>
+static cudaError_t launch_cfg(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
+{
+    constexpr int SMEM = D ? 0 : (W * S * 2048 + W * S * 8);
+    static bool attrSet[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (SMEM > 48 * 1024 && (dev < 0 || dev >= 64 || !attrSet[dev])) {
+        cudaError_t e = cudaFuncSetAttribute(dct32_imma_kernel<W, S, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attrSet[dev] = true;
+    }
+    const size_t want = (nBlocks + W - 1) / W;
+    const size_t cap = (size_t)sm_count() * B;
+    dct32_imma_kernel<W, S, B, D><<<(int)(want < cap ? want : cap), W * 32, SMEM, st>>>(src, dst, nBlocks, s1, s2);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_dct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
 {
     if (nBlocks == 0) return cudaSuccess;
-    static bool attrSet[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attrSet[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(dct32_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IMMA_SMEM);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attrSet[dev] = true;
+    switch (g_immaCfg) {
+    case 0: return launch_cfg<8, 4, 2, false>(src, dst, nBlocks, s1, s2, st);
+    case 1: return launch_cfg<8, 3, 3, false>(src, dst, nBlocks, s1, s2, st);
+    case 2: return launch_cfg<4, 4, 6, false>(src, dst, nBlocks, s1, s2, st);
+    case 3: return launch_cfg<8, 6, 2, false>(src, dst, nBlocks, s1, s2, st);
+    case 4: return launch_cfg<8, 2, 2, false>(src, dst, nBlocks, s1, s2, st);
+    case 5: return launch_cfg<16, 3, 1, false>(src, dst, nBlocks, s1, s2, st);
+    default:
+    case 6: return launch_cfg<8, 1, 2, true>(src, dst, nBlocks, s1, s2, st);
+    case 7: return launch_cfg<8, 1, 3, true>(src, dst, nBlocks, s1, s2, st);
+    case 8: return launch_cfg<4, 4, 5, false>(src, dst, nBlocks, s1, s2, st);
+    case 9: return launch_cfg<12, 3, 2, false>(src, dst, nBlocks, s1, s2, st);
+    case 10: return launch_cfg<4, 6, 4, false>(src, dst, nBlocks, s1, s2, st);
+    case 11: return launch_cfg<4, 1, 6, true>(src, dst, nBlocks, s1, s2, st);
     }
-    size_t want = (nBlocks + IMMA_WARPS - 1) / IMMA_WARPS;
-    size_t cap = (size_t)sm_count() * 2;
-    const int grid = (int)(want < cap ? want : cap);
-    dct32_imma_kernel<<<grid, IMMA_WARPS * 32, IMMA_SMEM, st>>>(src, dst, nBlocks, s1, s2);
-    count_launch();
-    return cudaGetLastError();
 }
 
 } // namespace x266

@@ -205,6 +205,13 @@ extern "C" int xGpuSetDctVariant(int variant)
     return 0;
 }
 
+extern "C" int xGpuTune(int key, int value)
+{
+    // diagnostic hook used by scripts/tune_dct.py; key 0 = IMMA kernel instantiation id
+    if (key == 0) { set_imma_config(value); return 0; }
+    return fail("xGpuTune: unknown key", cudaSuccess);
+}
+
 extern "C" int xDct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int s1, int s2, void* stream)
 {
     if (!shifts_ok(s1, s2) || (nBlocks && (!dSrc || !dDst))) return fail("xDct32BatchDev", cudaSuccess);

@@ -32,52 +32,85 @@ __device__ __forceinline__ void had8(int* v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Batch: n candidates of 64 int16 (128 B) -> n int32.  One candidate per thread; each warp stages its
-// 32 candidates (4 KiB) with coalesced 128-bit loads into a 128B-XOR-swizzled shared tile so that the
-// per-thread 128-bit row reads are bank-conflict free.
+// Batch: n candidates of 64 int16 (128 B) -> n int32.  One candidate per thread.  Each warp owns a ring
+// of STAGES x 4 KiB shared-memory slots (32 candidates) filled by 1-D TMA bulk copies, so the HBM
+// stream is decoupled from the ~580 integer ops a candidate costs.
+// Bank conflicts: lane L owns bytes [128L, 128L+128) of the slot, so a plain "row r" read would be an
+// 8-way conflict.  Instead lane L reads row (r ^ (L&7)) as its r-th row.  XOR-permuting the rows of
+// the 8x8 block by c only flips the sign of Hadamard output row k by (-1)^popcount(k&c), which the
+// abs() removes (and -x wraps to the same |x| in int16), so the cost is unchanged and the reads are
+// conflict free with a linear (un-swizzled) TMA destination.
 // ------------------------------------------------------------------------------------------------
-constexpr int SATD_WARPS = 8;
+constexpr int SATD_WARPS = 4;
+constexpr int SATD_STAGES = 3;
+constexpr int SATD_SMEM = SATD_WARPS * SATD_STAGES * 4096 + SATD_WARPS * SATD_STAGES * 8;
 
-__global__ void __launch_bounds__(SATD_WARPS * 32)
+__global__ void __launch_bounds__(SATD_WARPS * 32, 4)
 satd8x8_batch_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
 {
-    __shared__ __align__(128) uint8_t sm[SATD_WARPS][4096];
+    extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t base = smem_u32(&sm[warp][0]);
+    const uint32_t ring = smem_u32(smem) + warp * (SATD_STAGES * 4096);
+    const uint32_t bars = smem_u32(smem) + SATD_WARPS * SATD_STAGES * 4096 + warp * (SATD_STAGES * 8);
     const size_t nGroups = (n + 31) / 32;
+    const size_t first = (size_t)blockIdx.x * SATD_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * SATD_WARPS;
+    const uint64_t policy = policy_evict_first();
 
-    for (size_t grp = (size_t)blockIdx.x * SATD_WARPS + warp; grp < nGroups; grp += (size_t)gridDim.x * SATD_WARPS) {
+    auto issue = [&](size_t grp, int s) {
+        const size_t c0 = grp * 32;
+        const uint32_t bytes = (uint32_t)(((n - c0) < 32 ? (n - c0) : 32) * 128);
+        mbar_arrive_expect_tx(bars + 8 * s, bytes);
+        bulk_g2s(ring + s * 4096, diff + c0 * 64, bytes, bars + 8 * s, policy);
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < SATD_STAGES; s++) mbar_init(bars + 8 * s, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+#pragma unroll
+        for (int s = 0; s < SATD_STAGES; s++)
+            if (first + (size_t)s * stride < nGroups) issue(first + (size_t)s * stride, s);
+    }
+    __syncwarp();
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (size_t grp = first; grp < nGroups; grp += stride) {
         const size_t c0 = grp * 32;
         const int valid = (int)((n - c0) < 32 ? (n - c0) : 32);
+        mbar_wait(bars + 8 * stage, parity);
+
+        int d[64];
+        const uint32_t mine = ring + stage * 4096 + lane * 128;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int gi = i * 32 + lane, cand = gi >> 3, chunk = gi & 7;
-            if (cand < valid)
-                st_shared_v4(base + cand * 128 + ((chunk ^ (cand & 7)) << 4),
-                             ld_global_stream(diff + (c0 + cand) * 64 + chunk * 8));
+        for (int r = 0; r < 8; r++) {
+            const uint4 v = ld_shared_v4(mine + ((r ^ (lane & 7)) << 4));
+            d[8 * r + 0] = (int)(short)(v.x & 0xFFFF); d[8 * r + 1] = (int)v.x >> 16;
+            d[8 * r + 2] = (int)(short)(v.y & 0xFFFF); d[8 * r + 3] = (int)v.y >> 16;
+            d[8 * r + 4] = (int)(short)(v.z & 0xFFFF); d[8 * r + 5] = (int)v.z >> 16;
+            d[8 * r + 6] = (int)(short)(v.w & 0xFFFF); d[8 * r + 7] = (int)v.w >> 16;
         }
         __syncwarp();
-        if (lane < valid) {
-            int d[64];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const uint4 v = ld_shared_v4(base + lane * 128 + ((r ^ (lane & 7)) << 4));
-                d[8 * r + 0] = (int)(short)(v.x & 0xFFFF); d[8 * r + 1] = (int)v.x >> 16;
-                d[8 * r + 2] = (int)(short)(v.y & 0xFFFF); d[8 * r + 3] = (int)v.y >> 16;
-                d[8 * r + 4] = (int)(short)(v.z & 0xFFFF); d[8 * r + 5] = (int)v.z >> 16;
-                d[8 * r + 6] = (int)(short)(v.w & 0xFFFF); d[8 * r + 7] = (int)v.w >> 16;
-                had8<1>(&d[8 * r]);                       // horizontal
+        if (lane == 0) {
+            const size_t ng = grp + (size_t)SATD_STAGES * stride;
+            if (ng < nGroups) {
+                fence_proxy_async();
+                issue(ng, stage);
             }
-            int sad = 0;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                had8<8>(&d[c]);                           // vertical
-#pragma unroll
-                for (int r = 0; r < 8; r++) sad += abs((int)(short)d[8 * r + c]);
-            }
-            out[c0 + lane] = (sad + 2) >> 2;
         }
-        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; r++) had8<1>(&d[8 * r]);       // horizontal
+        int sad = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            had8<8>(&d[c]);                                   // vertical (rows XOR-permuted, see above)
+#pragma unroll
+            for (int r = 0; r < 8; r++) sad += abs((int)(short)d[8 * r + c]);
+        }
+        if (lane < valid) out[c0 + lane] = (sad + 2) >> 2;
+        if (++stage == SATD_STAGES) { stage = 0; parity ^= 1; }
     }
 }
 
@@ -200,9 +233,17 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    static bool attrSet[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attrSet[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(satd8x8_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SATD_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attrSet[dev] = true;
+    }
     size_t want = (n + SATD_WARPS * 32 - 1) / (SATD_WARPS * 32);
     size_t cap = (size_t)sm_count() * 4;
-    satd8x8_batch_kernel<<<(int)(want < cap ? want : cap), SATD_WARPS * 32, 0, st>>>(diff, out, n);
+    satd8x8_batch_kernel<<<(int)(want < cap ? want : cap), SATD_WARPS * 32, SATD_SMEM, st>>>(diff, out, n);
     count_launch();
     return cudaGetLastError();
 }
