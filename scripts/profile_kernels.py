@@ -29,5 +29,8 @@ cost = torch.empty((nb, 65, 65), device=dev, dtype=torch.int32)
 best = torch.empty((nb, 3), device=dev, dtype=torch.int32)
 for _ in range(2):
     xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+xb.tune(1, 1)
+xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+xb.tune(1, 0)
 torch.cuda.synchronize()
 print("profile driver done")

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Times the two full-search kernels on config 3 (1920x1080, +-32)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import x266_b200 as xb
+dev = torch.device("cuda:0")
+w, h, rg = 1920, 1080, 32
+cur = torch.randint(0, 256, (h, w), device=dev, dtype=torch.uint8)
+refp = torch.randint(0, 256, (h + 64, w + 64), device=dev, dtype=torch.uint8)
+nb = 240 * 135
+cost = torch.empty((nb, 65, 65), device=dev, dtype=torch.int32)
+best = torch.empty((nb, 3), device=dev, dtype=torch.int32)
+st = torch.cuda.current_stream().cuda_stream
+outs = {}
+for v1 in (1, 0):
+    xb.tune(1, v1)
+    for with_cost in (True, False):
+        c = cost.data_ptr() if with_cost else 0
+        for _ in range(2):
+            xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c, best.data_ptr(), st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c, best.data_ptr(), st)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"search {'v1' if v1 else 'v2'} cost_surface={with_cost}: {ms:.3f} ms/frame  {nb*4225/ms/1e6:.1f} G cand/s", flush=True)
+        if with_cost: outs[v1] = (cost.clone(), best.clone())
+print("v1 == v2:", torch.equal(outs[0][0], outs[1][0]), torch.equal(outs[0][1], outs[1][1]))
+xb.tune(1, 0)

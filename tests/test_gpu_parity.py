@@ -192,13 +192,37 @@ def make_frames(w, h, rng_px, seed=266):
     return cur, np.pad(ref, rng_px, mode="edge")
 
 
-@pytest.mark.parametrize("rng_px", [0, 3, 8, 32])
-def test_satd_search_small(x266, orc, rng_px):
+@pytest.mark.parametrize("rng_px", [0, 3, 8, 16, 32])
+@pytest.mark.parametrize("v1", [0, 1])
+def test_satd_search_small(x266, orc, rng_px, v1):
+    """both search kernels (v1: CTA per block; v2: transform-domain strips, R in {8,16,32})"""
+    x266.tune(1, v1)
     cur, refp = make_frames(64, 48, rng_px)
     cost, best = x266.xSatd8x8Search(cur, refp, rng_px)
+    x266.tune(1, 0)
     wc, wb = orc.satd_search(cur, refp, rng_px, 0, 48)
     assert np.array_equal(cost, wc)
     assert np.array_equal(best, wb)
+
+
+@pytest.mark.parametrize("rng_px", [8, 32])
+def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px):
+    """width 200 = one full strip of 16 blocks + a ragged strip of 9; block sub-ranges that start and end
+    mid-strip / mid-row; extreme flat frames (all ties -> the tie-break rule decides)."""
+    cur, refp = make_frames(200, 24, rng_px, seed=5)
+    nblk = 25 * 3
+    wc, wb = orc.satd_search(cur, refp, rng_px, 0, nblk)
+    cost, best = x266.xSatd8x8Search(cur, refp, rng_px)
+    assert np.array_equal(cost, wc) and np.array_equal(best, wb)
+    for b0, b1 in ((3, 4), (14, 19), (20, 60), (74, 75)):
+        c, b = x266.xSatd8x8Search(cur, refp, rng_px, b0, b1)
+        assert np.array_equal(c, wc[b0:b1]) and np.array_equal(b, wb[b0:b1])
+        _, b = x266.xSatd8x8Search(cur, refp, rng_px, b0, b1, want_cost=False)
+        assert np.array_equal(b, wb[b0:b1])
+    flat = np.full((24, 200), 200, np.uint8)
+    flatp = np.full((24 + 2 * rng_px, 200 + 2 * rng_px), 10, np.uint8)
+    c, b = x266.xSatd8x8Search(flat, flatp, rng_px)
+    assert (b[:, 1] == 0).all() and (b[:, 2] == 0).all() and (c == c[0, 0, 0]).all()
 
 
 def test_satd_search_1080p_sample(x266, orc):

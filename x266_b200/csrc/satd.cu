@@ -230,6 +230,168 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Full search v2 (R in {8,16,32}): transform-domain, one CTA per strip of NB=16 horizontally adjacent
+// blocks.  For every search row my the CTA computes, once, the full 2-D Hadamard T[p] of the reference
+// window at each of the P = 8*(NB-1)+2R+1 horizontal positions p (thread p keeps its 64 coefficients in
+// registers: vertical half V from the smem window, horizontal half from V).  Position p serves every
+// block i of the strip with 0 <= p-8i <= 2R, i.e. at most R/4+1 blocks ("slots"); the cost of candidate
+// (i, mx=p-8i, my) is sum_k |T[p][k] - Tcur_i[k]| (exact: 8-bit pixels cannot wrap int16), 64 VABSDIFF
+// fed by 16 broadcast-ish 128-bit smem loads of Tcur_i.  ~130 instructions per candidate instead of
+// ~300 (v1) / 577 (direct), and the 2R+1 = 65 candidates-per-row raggedness costs 10 % of the lanes
+// instead of 33 %.
+// ------------------------------------------------------------------------------------------------
+constexpr int S2_NB = 16;
+constexpr int S2_TC_STRIDE = 68;     // 64 coefficients + 4 words of padding: distinct blocks hit distinct banks
+
+template <int R>
+__global__ void __launch_bounds__(((8 * S2_NB + 2 * R + 31) / 32) * 32)
+satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w,
+                         size_t blk0, size_t blk1, uint32_t* __restrict__ cost, int32_t* __restrict__ best)
+{
+    constexpr int COLS = 8 * S2_NB + 2 * R;
+    constexpr int NT = ((COLS + 31) / 32) * 32;
+    constexpr int SIDE = 2 * R + 1;
+    constexpr int WS = 2 * R + 8;
+    constexpr int SLOTS = R / 4 + 1;
+    __shared__ uint8_t win[WS][COLS];
+    __shared__ int V[2][8][COLS];
+    __shared__ __align__(16) int tcur[S2_NB][S2_TC_STRIDE];
+    __shared__ unsigned long long sBest[S2_NB];
+
+    const int tid = threadIdx.x;
+    const int bw = w >> 3;
+    const int i0 = blockIdx.x * S2_NB;
+    const int nb = (bw - i0) < S2_NB ? (bw - i0) : S2_NB;
+    const int by = blockIdx.y * 8, bx0 = i0 * 8;
+    const size_t bFirst = (size_t)blockIdx.y * bw + i0;
+    if (bFirst + nb <= blk0 || bFirst >= blk1) return;
+    const int cols = 8 * nb + 2 * R;
+    const int nPos = 8 * (nb - 1) + 2 * R + 1;
+
+    const uint8_t* wsrc = refPad + (intptr_t)by * strd + bx0;
+    for (int idx = tid; idx < WS * COLS; idx += NT) {
+        const int yy = idx / COLS, xx = idx - yy * COLS;
+        win[yy][xx] = xx < cols ? wsrc[(intptr_t)yy * strd + xx] : (uint8_t)0;
+    }
+    if (tid < S2_NB) sBest[tid] = ~0ull;
+    if (tid < nb * 8) {                              // horizontal transform of row (tid&7) of block (tid>>3)
+        const int i = tid >> 3, r = tid & 7;
+        int v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[c] = cur[(size_t)(by + r) * w + bx0 + 8 * i + c];
+        had8<1>(v);
+#pragma unroll
+        for (int c = 0; c < 8; c++) tcur[i][r * 8 + c] = v[c];
+    }
+    __syncthreads();
+    if (tid < nb * 8) {                              // vertical transform of column (tid&7) of block (tid>>3)
+        const int i = tid >> 3, c = tid & 7;
+        int v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = tcur[i][r * 8 + c];
+        had8<1>(v);
+#pragma unroll
+        for (int r = 0; r < 8; r++) tcur[i][r * 8 + c] = v[r];
+    }
+    // (the __syncthreads inside the first loop iteration orders these writes before any read)
+
+    const int p = tid;
+    int iLo = (p - 2 * R + 7) >> 3;
+    iLo = iLo < 0 ? 0 : iLo;
+    const int iHi = (p >> 3) < (nb - 1) ? (p >> 3) : (nb - 1);
+    unsigned long long bestKey[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++) bestKey[s] = ~0ull;
+
+    for (int my = 0; my < SIDE; my++) {
+        if (tid < COLS) {
+            int v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = win[my + i][tid];
+            had8<1>(v);
+#pragma unroll
+            for (int r = 0; r < 8; r++) V[my & 1][r][tid] = v[r];
+        }
+        __syncthreads();
+        if (p < nPos) {
+            int T[64];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) T[r * 8 + c] = V[my & 1][r][p + c];
+                had8<1>(&T[r * 8]);
+            }
+            const int dy = my - R;
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                const int i = iLo + s;
+                if (i <= iHi) {
+                    const int4* tc = reinterpret_cast<const int4*>(&tcur[i][0]);
+                    unsigned sad = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const int4 c = tc[k];
+                        sad = __sad(T[4 * k + 0], c.x, sad);
+                        sad = __sad(T[4 * k + 1], c.y, sad);
+                        sad = __sad(T[4 * k + 2], c.z, sad);
+                        sad = __sad(T[4 * k + 3], c.w, sad);
+                    }
+                    const unsigned c4 = (sad + 2) >> 2;
+                    const int mx = p - 8 * i;
+                    const size_t b = bFirst + i;
+                    if (b >= blk0 && b < blk1) {
+                        if (cost) cost[((b - blk0) * SIDE + my) * SIDE + mx] = c4;
+                        const int dx = mx - R;
+                        const unsigned long long key = ((unsigned long long)c4 << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
+                                                       ((unsigned long long)my << 12) | (unsigned long long)mx;
+                        bestKey[s] = key < bestKey[s] ? key : bestKey[s];
+                    }
+                }
+            }
+        }
+    }
+    if (best) {
+        if (p < nPos) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++) {
+                const int i = iLo + s;
+                if (i <= iHi && bestKey[s] != ~0ull) atomicMin(&sBest[i], bestKey[s]);
+            }
+        }
+        __syncthreads();
+        if (tid < nb) {
+            const size_t b = bFirst + tid;
+            if (b >= blk0 && b < blk1) {
+                const unsigned long long k = sBest[tid];
+                int32_t* o = best + (b - blk0) * 3;
+                o[0] = (int32_t)(k >> 40);
+                o[1] = (int)(k & 0xFFF) - R;
+                o[2] = (int)((k >> 12) & 0xFFF) - R;
+            }
+        }
+    }
+}
+
+static int g_searchV1 = 0;
+void set_search_v1(int on) { g_searchV1 = on; }
+
+template <int R>
+static cudaError_t launch_search_v2(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h,
+                                    size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
+{
+    const int bw = w / 8, bh = h / 8;
+    const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
+    (void)bh;
+    // grid.y starts at block-row 0; CTAs outside [blk0, blk1) exit immediately
+    dim3 grid((bw + S2_NB - 1) / S2_NB, y1 + 1);
+    (void)y0;
+    constexpr int NT = ((8 * S2_NB + 2 * R + 31) / 32) * 32;
+    satd8x8_search_v2_kernel<R><<<grid, NT, 0, st>>>(cur, refPad, strd, w, blk0, blk1, cost, best);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
@@ -253,6 +415,11 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
 {
     if (blk1 <= blk0) return cudaSuccess;
     if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
+    if (!g_searchV1) {
+        if (range == 32) return launch_search_v2<32>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
+        if (range == 16) return launch_search_v2<16>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
+        if (range == 8) return launch_search_v2<8>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
+    }
     const int ws = 2 * range + 8, wsp = (ws + 3) & ~3;
     const size_t smem = 128 * sizeof(int) + (size_t)SRCH_WARPS * 8 * wsp * sizeof(int) + (size_t)ws * wsp;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
