@@ -6,7 +6,7 @@ import torch
 import x266_b200 as xb
 
 CFG = {0: "W8 S4 B2 ring", 1: "W8 S3 B3 ring", 2: "W4 S4 B6 ring", 3: "W8 S6 B2 ring", 4: "W8 S2 B2 ring", 5: "W16 S3 B1 ring",
-       6: "W8 B2 direct", 7: "W8 B3 direct", 8: "W4 S4 B5 ring", 9: "W12 S3 B2 ring", 10: "W4 S6 B4 ring", 11: "W4 B6 direct"}
+       6: "W8 B2 direct", 7: "W8 B3 direct", 8: "W4 S4 B5 ring", 9: "W12 S3 B2 ring", 10: "W4 S6 B4 ring", 11: "W4 B6 direct", 12: "W8 B2 direct d2", 13: "W8 B2 direct d3", 14: "W4 B4 direct d2", 15: "W16 B1 direct d2"}
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = torch.device("cuda:0")
 n = frames * 32400
@@ -18,7 +18,7 @@ xb.set_dct_variant(xb.DCT_BFLY)
 xb.xDct32BatchDev(src.data_ptr(), ref.data_ptr(), n, 6, 11, st)
 xb.set_dct_variant(xb.DCT_IMMA)
 res = {}
-for rep in range(2):
+for rep in range(1):
     for cfg, name in CFG.items():
         xb.tune(0, cfg)
         dst.zero_()

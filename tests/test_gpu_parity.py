@@ -158,8 +158,15 @@ def test_dctN(x266, orc, log2n, nblk):
 
 
 # ---------------------------------------------------------------------------------------- SATD
+@pytest.fixture(params=["imma", "cuda-core"])
+def satd_variant(request, x266):
+    x266.tune(2, 1 if request.param == "cuda-core" else 0)
+    yield request.param
+    x266.tune(2, 0)
+
+
 @pytest.mark.parametrize("name", ["KAT-D", "KAT-E"])
-def test_satd_kat(x266, orc, kat, name):
+def test_satd_kat(x266, orc, kat, name, satd_variant):
     k = kat[name]
     x = orc.residual(k["blocks"] * 64, k["seed"], k["kind"])
     y = x266.xSatd8x8Batch(x)
@@ -167,8 +174,8 @@ def test_satd_kat(x266, orc, kat, name):
     assert f"{orc.fnv(y):016x}" == k["fnv_out"]
 
 
-@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 257, 100003, (1 << 17) + 3])
-def test_satd_ragged(x266, orc, n):
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 255, 257, 100003, (1 << 17) + 3])
+def test_satd_ragged(x266, orc, n, satd_variant):
     x = orc.residual(n * 64, n + 1, 2)
     y = x266.xSatd8x8Batch(x)
     assert y.shape == (n,)
@@ -176,7 +183,7 @@ def test_satd_ragged(x266, orc, n):
         assert np.array_equal(y, orc.satd(x, threads=8))
 
 
-def test_satd_reference_vectors_and_extremes(x266, vectors):
+def test_satd_reference_vectors_and_extremes(x266, vectors, satd_variant):
     assert np.array_equal(x266.xSatd8x8Batch(vectors["satd_in"]), vectors["satd_out"])
     assert int(x266.xSatd8x8Batch(np.full(64, 255, np.int16))[0]) == 4080
     assert int(x266.xSatd8x8Batch(np.full(64, -32768, np.int16))[0]) == int(vectors["satd_out"][66])

@@ -151,6 +151,24 @@ __device__ __forceinline__ void mma_s8s8(int (&d)[4], const uint32_t (&a)[4], ui
           "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
 }
 
+// D(16x8,s32) = A(16x32,u8,row) * B(32x8,s8,col) + C   (data on the A side, +-1 Hadamard matrix on the B side)
+__device__ __forceinline__ void mma_u8s8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const int (&c)[4])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1),
+          "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+}
+
+__device__ __forceinline__ uint4 ld_global_nc(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
     uint32_t r;

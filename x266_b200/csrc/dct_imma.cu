@@ -89,7 +89,7 @@ dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, si
     const size_t first = (size_t)blockIdx.x * IMMA_WARPS + warp;
     const size_t stride = (size_t)gridDim.x * IMMA_WARPS;
     uint64_t policy = 0;
-    uint4 nxt[4] = {};
+    uint4 nxt[DIRECT ? IMMA_STAGES : 1][4] = {};      // DIRECT: blocks b+stride .. b+STAGES*stride in flight
 
     if constexpr (!DIRECT) {
         policy = policy_evict_first();
@@ -109,9 +109,13 @@ dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, si
         }
         __syncwarp();
     } else {
-        if (first < nBlocks) {
 #pragma unroll
-            for (int t = 0; t < 4; t++) nxt[t] = ld_global_stream(src + first * 1024 + t * 256 + lane * 8);
+        for (int s = 0; s < IMMA_STAGES; s++) {
+            const size_t b = first + (size_t)s * stride;
+            if (b < nBlocks) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) nxt[s][t] = ld_global_stream(src + b * 1024 + t * 256 + lane * 8);
+            }
         }
     }
 
@@ -145,14 +149,18 @@ dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, si
         } else {
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                const uint4 w = nxt[t];
+                const uint4 w = nxt[0][t];
                 BL[t][0] = prmt(w.x, w.y, 0x6420); BH[t][0] = prmt(w.x, w.y, 0x7531);
                 BL[t][1] = prmt(w.z, w.w, 0x6420); BH[t][1] = prmt(w.z, w.w, 0x7531);
             }
-            const size_t nb = b + stride;
+#pragma unroll
+            for (int s = 0; s + 1 < IMMA_STAGES; s++)
+#pragma unroll
+                for (int t = 0; t < 4; t++) nxt[s][t] = nxt[s + 1][t];
+            const size_t nb = b + (size_t)IMMA_STAGES * stride;
             if (nb < nBlocks) {
 #pragma unroll
-                for (int t = 0; t < 4; t++) nxt[t] = ld_global_stream(src + nb * 1024 + t * 256 + lane * 8);
+                for (int t = 0; t < 4; t++) nxt[IMMA_STAGES - 1][t] = ld_global_stream(src + nb * 1024 + t * 256 + lane * 8);
             }
         }
 
@@ -253,6 +261,10 @@ cudaError_t launch_dct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, 
     case 9: return launch_cfg<12, 3, 2, false>(src, dst, nBlocks, s1, s2, st);
     case 10: return launch_cfg<4, 6, 4, false>(src, dst, nBlocks, s1, s2, st);
     case 11: return launch_cfg<4, 1, 6, true>(src, dst, nBlocks, s1, s2, st);
+    case 12: return launch_cfg<8, 2, 2, true>(src, dst, nBlocks, s1, s2, st);
+    case 13: return launch_cfg<8, 3, 2, true>(src, dst, nBlocks, s1, s2, st);
+    case 14: return launch_cfg<4, 2, 4, true>(src, dst, nBlocks, s1, s2, st);
+    case 15: return launch_cfg<16, 2, 1, true>(src, dst, nBlocks, s1, s2, st);
     }
 }
 

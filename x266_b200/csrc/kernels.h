@@ -12,6 +12,7 @@ void count_launch();            // bumps the library-wide kernel launch counter
 cudaError_t launch_dct32_bfly(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 cudaError_t launch_dct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 void set_imma_config(int id);   // tuning/diagnostic: selects a (warps, stages, CTAs/SM, staging) instantiation
+void set_satd_cuda_cores(int on);   // tuning/diagnostic: CUDA-core SATD batch kernel instead of IMMA
 void set_search_v1(int on);     // tuning/diagnostic: force the v1 (one CTA per block) search kernel
 cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int line, cudaStream_t st);
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);

@@ -115,6 +115,106 @@ satd8x8_batch_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batch on the int8 tensor cores (shipped default).  The 2-D Hadamard of an 8x8 block is the 64x64
+// Sylvester matrix H64[n][p] = (-1)^popcount(n&p) applied to the 64 samples, so for 16 candidates at a
+// time   D[cand][n] = sum_p diff[cand][p] * H64[n][p]   is an m16 x n64 x k64 integer product.  As in the
+// DCT kernel the int16 samples are split into byte planes (lo u8, hi s8; +-1 fits s8):
+//     D = D_lo + 256 * D_hi     (exact in s32; only D mod 2^16 matters = the reference's int16 wrap)
+// 32 x mma.sync.m16n8k32 per 16 candidates (2 k-steps x 8 n-tiles x 2 planes).  The candidate rows are
+// the A operand, read straight from global memory with 128-bit loads (row-major A == the 128-byte
+// candidate), register double-buffered; the K order is permuted so that each lane's A registers come
+// from one 16-byte chunk (the +-1 matrix columns are permuted to match, held in 32 registers).
+// Epilogue per lane: 32 coefficients -> IMAD (lo + 256 hi), sign-extend 16, VABSDIFF-accumulate; a quad
+// shuffle reduction gives the two costs of rows g and g+8.   ~10 warp instructions per candidate instead
+// of ~24 on CUDA cores (759 thread instructions per candidate measured, ALU-pipe bound at 77 %).
+// ------------------------------------------------------------------------------------------------
+constexpr int SATDI_WARPS = 8;
+
+__global__ void __launch_bounds__(SATDI_WARPS * 32, 2)
+satd8x8_imma_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+
+    // B fragments of the permuted +-1 matrix: k-step s, n-tile t; K position 4q+i <-> sample 32s+8q+i,
+    // K position 16+4q+i <-> sample 32s+8q+4+i; column n = 8t+g.
+    uint32_t B[2][8][2];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int pix = 32 * s + 8 * q + 4 * r + i;
+                    const int nn = 8 * t + g;
+                    v |= ((__popc(nn & pix) & 1) ? 0xFFu : 0x01u) << (8 * i);
+                }
+                B[s][t][r] = v;
+            }
+
+    const size_t nUnits = (n + 15) / 16;
+    const size_t first = (size_t)blockIdx.x * SATDI_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * SATDI_WARPS;
+    const int cZero[4] = { 0, 0, 0, 0 };
+
+    // lane loads: row g and row g+8 of the unit, 16-byte chunk q of each 64-byte half s
+    auto load_unit = [&](size_t u, uint4 (&w)[2][2]) {
+        size_t c0 = u * 16 + g, c1 = c0 + 8;
+        c0 = c0 < n ? c0 : n - 1;           // clamp the ragged tail (results of clamped rows are not stored)
+        c1 = c1 < n ? c1 : n - 1;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            w[s][0] = ld_global_nc(diff + c0 * 64 + 32 * s + 8 * q);
+            w[s][1] = ld_global_nc(diff + c1 * 64 + 32 * s + 8 * q);
+        }
+    };
+
+    uint4 nxt[2][2] = {};
+    if (first < nUnits) load_unit(first, nxt);
+
+    for (size_t u = first; u < nUnits; u += stride) {
+        // A fragments per plane and k-step: a0 (row g, K 4q+i), a1 (row g+8, same K), a2 (row g, K 16+4q+i), a3 (row g+8)
+        uint32_t AL[2][4], AH[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const uint4 r0 = nxt[s][0], r1 = nxt[s][1];
+            AL[s][0] = prmt(r0.x, r0.y, 0x6420); AH[s][0] = prmt(r0.x, r0.y, 0x7531);
+            AL[s][2] = prmt(r0.z, r0.w, 0x6420); AH[s][2] = prmt(r0.z, r0.w, 0x7531);
+            AL[s][1] = prmt(r1.x, r1.y, 0x6420); AH[s][1] = prmt(r1.x, r1.y, 0x7531);
+            AL[s][3] = prmt(r1.z, r1.w, 0x6420); AH[s][3] = prmt(r1.z, r1.w, 0x7531);
+        }
+        if (u + stride < nUnits) load_unit(u + stride, nxt);
+
+        unsigned s0a = 0, s0b = 0, s1a = 0, s1b = 0;      // row g (c0,c1) and row g+8 (c2,c3), two chains each
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            int dl[4], dh[4];
+            mma_u8s8(dl, AL[0], B[0][t][0], B[0][t][1], cZero);
+            mma_u8s8(dl, AL[1], B[1][t][0], B[1][t][1], dl);
+            mma_s8s8(dh, AH[0], B[0][t][0], B[0][t][1], cZero);
+            mma_s8s8(dh, AH[1], B[1][t][0], B[1][t][1], dh);
+            const int v0 = (int)(short)(dl[0] + dh[0] * 256);
+            const int v1 = (int)(short)(dl[1] + dh[1] * 256);
+            const int v2 = (int)(short)(dl[2] + dh[2] * 256);
+            const int v3 = (int)(short)(dl[3] + dh[3] * 256);
+            s0a = __sad(v0, 0, s0a); s0b = __sad(v1, 0, s0b);
+            s1a = __sad(v2, 0, s1a); s1b = __sad(v3, 0, s1b);
+        }
+        unsigned sad0 = s0a + s0b, sad1 = s1a + s1b;
+        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 1); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 1);
+        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 2); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 2);
+        if (q == 0) {
+            const size_t c0 = u * 16 + g;
+            if (c0 < n) out[c0] = (int)((sad0 + 2) >> 2);
+            if (c0 + 8 < n) out[c0 + 8] = (int)((sad1 + 2) >> 2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Full search.  One CTA per 8x8 current block; the (8+2R)^2 reference window lives in shared memory.
 // Linearity (exact here: 8-bit pixels give |coef| <= 16320, no int16 wrap is reachable) lets the
 // transform of the current block be computed once, and the vertical half of each reference-window
@@ -190,7 +290,7 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
         }
         __syncwarp();
         for (int mx = lane; mx < side; mx += 32) {
-            unsigned sad = 0;
+            unsigned sa = 0, sb = 0;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 int v[8];
@@ -198,9 +298,12 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
                 for (int c = 0; c < 8; c++) v[c] = V[r * wsp + mx + c];
                 had8<1>(v);
 #pragma unroll
-                for (int c = 0; c < 8; c++) sad = __sad(v[c], tc[r * 8 + c], sad);
+                for (int c = 0; c < 8; c += 2) {
+                    sa = __sad(v[c], tc[r * 8 + c], sa);
+                    sb = __sad(v[c + 1], tc[r * 8 + c + 1], sb);
+                }
             }
-            const unsigned c4 = (sad + 2) >> 2;
+            const unsigned c4 = (sa + sb + 2) >> 2;
             if (costBlk) costBlk[my * side + mx] = c4;
             const int dx = mx - range, dy = my - range;
             const unsigned long long key = ((unsigned long long)c4 << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
@@ -243,23 +346,25 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
 // ------------------------------------------------------------------------------------------------
 constexpr int S2_NB = 16;
 constexpr int S2_TC_STRIDE = 68;     // 64 coefficients + 4 words of padding: distinct blocks hit distinct banks
+constexpr int S2_VW = 40;            // per-warp V tile: 32 positions + 7 halo columns (+1 pad)
 
-template <int R>
-__global__ void __launch_bounds__(((8 * S2_NB + 2 * R + 31) / 32) * 32)
+template <int R, int MINB>
+__global__ void __launch_bounds__(((8 * S2_NB + 2 * R + 31) / 32) * 32, MINB)
 satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w,
                          size_t blk0, size_t blk1, uint32_t* __restrict__ cost, int32_t* __restrict__ best)
 {
     constexpr int COLS = 8 * S2_NB + 2 * R;
     constexpr int NT = ((COLS + 31) / 32) * 32;
+    constexpr int NW = NT / 32;
     constexpr int SIDE = 2 * R + 1;
     constexpr int WS = 2 * R + 8;
     constexpr int SLOTS = R / 4 + 1;
-    __shared__ uint8_t win[WS][COLS];
-    __shared__ int V[2][8][COLS];
+    __shared__ uint8_t win[WS][COLS + 8];
+    __shared__ int V[NW][8][S2_VW];
     __shared__ __align__(16) int tcur[S2_NB][S2_TC_STRIDE];
     __shared__ unsigned long long sBest[S2_NB];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bw = w >> 3;
     const int i0 = blockIdx.x * S2_NB;
     const int nb = (bw - i0) < S2_NB ? (bw - i0) : S2_NB;
@@ -270,8 +375,8 @@ satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     const int nPos = 8 * (nb - 1) + 2 * R + 1;
 
     const uint8_t* wsrc = refPad + (intptr_t)by * strd + bx0;
-    for (int idx = tid; idx < WS * COLS; idx += NT) {
-        const int yy = idx / COLS, xx = idx - yy * COLS;
+    for (int idx = tid; idx < WS * (COLS + 8); idx += NT) {
+        const int yy = idx / (COLS + 8), xx = idx - yy * (COLS + 8);
         win[yy][xx] = xx < cols ? wsrc[(intptr_t)yy * strd + xx] : (uint8_t)0;
     }
     if (tid < S2_NB) sBest[tid] = ~0ull;
@@ -294,71 +399,93 @@ satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
 #pragma unroll
         for (int r = 0; r < 8; r++) tcur[i][r * 8 + c] = v[r];
     }
-    // (the __syncthreads inside the first loop iteration orders these writes before any read)
+    __syncthreads();
 
+    // From here on every warp runs on its own: it owns positions [32*warp, 32*warp+32) and computes the
+    // vertical transforms of the 39 window columns those positions touch (7 halo columns recomputed).
     const int p = tid;
-    int iLo = (p - 2 * R + 7) >> 3;
-    iLo = iLo < 0 ? 0 : iLo;
-    const int iHi = (p >> 3) < (nb - 1) ? (p >> 3) : (nb - 1);
-    unsigned long long bestKey[SLOTS];
+    if (warp * 32 < nPos) {
+        int iLo = (p - 2 * R + 7) >> 3;
+        iLo = iLo < 0 ? 0 : iLo;
+        const int iHi = (p >> 3) < (nb - 1) ? (p >> 3) : (nb - 1);
+        // per-slot running best, 32-bit: cost << 7 | rank(my), rank orders dy by |dy| then sign (negative first);
+        // mx is fixed per slot, so this is the full tie-break rule restricted to the slot.
+        unsigned bestKey[SLOTS];
 #pragma unroll
-    for (int s = 0; s < SLOTS; s++) bestKey[s] = ~0ull;
+        for (int s = 0; s < SLOTS; s++) bestKey[s] = 0xFFFFFFFFu;
+        int (*Vw)[S2_VW] = V[warp];
+        const int c0 = warp * 32;
 
-    for (int my = 0; my < SIDE; my++) {
-        if (tid < COLS) {
-            int v[8];
+        for (int my = 0; my < SIDE; my++) {
+            {
+                int v[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = win[my + i][tid];
-            had8<1>(v);
+                for (int i = 0; i < 8; i++) v[i] = win[my + i][c0 + lane];
+                had8<1>(v);
 #pragma unroll
-            for (int r = 0; r < 8; r++) V[my & 1][r][tid] = v[r];
-        }
-        __syncthreads();
-        if (p < nPos) {
-            int T[64];
+                for (int r = 0; r < 8; r++) Vw[r][lane] = v[r];
+                if (lane < 7) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
+                    for (int i = 0; i < 8; i++) v[i] = win[my + i][c0 + 32 + lane];
+                    had8<1>(v);
 #pragma unroll
-                for (int c = 0; c < 8; c++) T[r * 8 + c] = V[my & 1][r][p + c];
-                had8<1>(&T[r * 8]);
+                    for (int r = 0; r < 8; r++) Vw[r][32 + lane] = v[r];
+                }
             }
-            const int dy = my - R;
+            __syncwarp();
+            if (p < nPos) {
+                int T[64];
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) T[r * 8 + c] = Vw[r][lane + c];
+                    had8<1>(&T[r * 8]);
+                }
+                const int dy = my - R;
+                const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) {
+                    const int i = iLo + s;
+                    if (i <= iHi) {
+                        const int4* tc = reinterpret_cast<const int4*>(&tcur[i][0]);
+                        unsigned sa = 0, sb = 0, sc = 0, sd = 0;       // 4 independent chains (VABSDIFF latency)
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const int4 c = tc[k];
+                            sa = __sad(T[4 * k + 0], c.x, sa);
+                            sb = __sad(T[4 * k + 1], c.y, sb);
+                            sc = __sad(T[4 * k + 2], c.z, sc);
+                            sd = __sad(T[4 * k + 3], c.w, sd);
+                        }
+                        const unsigned c4 = ((sa + sb) + (sc + sd) + 2) >> 2;
+                        const size_t b = bFirst + i;
+                        if (b >= blk0 && b < blk1) {
+                            if (cost) cost[((b - blk0) * SIDE + my) * SIDE + (p - 8 * i)] = c4;
+                            const unsigned key = (c4 << 7) | rank;
+                            bestKey[s] = key < bestKey[s] ? key : bestKey[s];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (best && p < nPos) {
 #pragma unroll
             for (int s = 0; s < SLOTS; s++) {
                 const int i = iLo + s;
-                if (i <= iHi) {
-                    const int4* tc = reinterpret_cast<const int4*>(&tcur[i][0]);
-                    unsigned sad = 0;
-#pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        const int4 c = tc[k];
-                        sad = __sad(T[4 * k + 0], c.x, sad);
-                        sad = __sad(T[4 * k + 1], c.y, sad);
-                        sad = __sad(T[4 * k + 2], c.z, sad);
-                        sad = __sad(T[4 * k + 3], c.w, sad);
-                    }
-                    const unsigned c4 = (sad + 2) >> 2;
-                    const int mx = p - 8 * i;
-                    const size_t b = bFirst + i;
-                    if (b >= blk0 && b < blk1) {
-                        if (cost) cost[((b - blk0) * SIDE + my) * SIDE + mx] = c4;
-                        const int dx = mx - R;
-                        const unsigned long long key = ((unsigned long long)c4 << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
-                                                       ((unsigned long long)my << 12) | (unsigned long long)mx;
-                        bestKey[s] = key < bestKey[s] ? key : bestKey[s];
-                    }
+                if (i <= iHi && bestKey[s] != 0xFFFFFFFFu) {
+                    const unsigned rank = bestKey[s] & 127u;
+                    const int dy = (rank & 1) ? -(int)((rank + 1) >> 1) : (int)(rank >> 1);
+                    const int mx = p - 8 * i, dx = mx - R, my = dy + R;
+                    const unsigned long long key = ((unsigned long long)(bestKey[s] >> 7) << 40) |
+                                                   ((unsigned long long)(dx * dx + dy * dy) << 24) |
+                                                   ((unsigned long long)my << 12) | (unsigned long long)mx;
+                    atomicMin(&sBest[i], key);
                 }
             }
         }
     }
     if (best) {
-        if (p < nPos) {
-#pragma unroll
-            for (int s = 0; s < SLOTS; s++) {
-                const int i = iLo + s;
-                if (i <= iHi && bestKey[s] != ~0ull) atomicMin(&sBest[i], bestKey[s]);
-            }
-        }
         __syncthreads();
         if (tid < nb) {
             const size_t b = bFirst + tid;
@@ -373,7 +500,7 @@ satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     }
 }
 
-static int g_searchV1 = 0;
+static int g_searchV1 = 0;      // 0: v2, 2 CTAs/SM register budget; 1: v1; 2: v2 squeezed to 3 CTAs/SM
 void set_search_v1(int on) { g_searchV1 = on; }
 
 template <int R>
@@ -387,14 +514,25 @@ static cudaError_t launch_search_v2(const uint8_t* cur, const uint8_t* refPad, i
     dim3 grid((bw + S2_NB - 1) / S2_NB, y1 + 1);
     (void)y0;
     constexpr int NT = ((8 * S2_NB + 2 * R + 31) / 32) * 32;
-    satd8x8_search_v2_kernel<R><<<grid, NT, 0, st>>>(cur, refPad, strd, w, blk0, blk1, cost, best);
+    if (g_searchV1 == 2) satd8x8_search_v2_kernel<R, 3><<<grid, NT, 0, st>>>(cur, refPad, strd, w, blk0, blk1, cost, best);
+    else satd8x8_search_v2_kernel<R, 2><<<grid, NT, 0, st>>>(cur, refPad, strd, w, blk0, blk1, cost, best);
     count_launch();
     return cudaGetLastError();
 }
 
+static int g_satdCuda = 0;      // tuning/diagnostic: 1 = CUDA-core batch kernel instead of the IMMA one
+void set_satd_cuda_cores(int on) { g_satdCuda = on; }
+
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    if (!g_satdCuda) {
+        size_t want = ((n + 15) / 16 + SATDI_WARPS - 1) / SATDI_WARPS;
+        size_t cap = (size_t)sm_count() * 2;
+        satd8x8_imma_kernel<<<(int)(want < cap ? want : cap), SATDI_WARPS * 32, 0, st>>>(diff, out, n);
+        count_launch();
+        return cudaGetLastError();
+    }
     static bool attrSet[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -415,7 +553,7 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
 {
     if (blk1 <= blk0) return cudaSuccess;
     if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
-    if (!g_searchV1) {
+    if (g_searchV1 != 1) {
         if (range == 32) return launch_search_v2<32>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
         if (range == 16) return launch_search_v2<16>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
         if (range == 8) return launch_search_v2<8>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
