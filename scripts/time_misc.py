@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Times the secondary kernels: DCT 4/8/16, one-pass partialButterfly32, intra32 (GB/s of algorithmic bytes)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import x266_b200 as xb
+dev = torch.device("cuda:0")
+st = torch.cuda.current_stream().cuda_stream
+def timeit(fn, reps=10):
+    for _ in range(3): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+nsamp = 1 << 30          # 1 Gi samples = 2 GiB in + 2 GiB out
+src = (torch.randint(0, 1024, (nsamp,), device=dev, dtype=torch.int16) - torch.randint(0, 1024, (nsamp,), device=dev, dtype=torch.int16))
+dst = torch.empty_like(src)
+for log2n, (s1, s2) in ((2, (1, 8)), (3, (2, 9)), (4, (3, 10)), (5, (4, 11))):
+    nb = nsamp >> (2 * log2n)
+    ms = timeit(lambda: xb.xDctNBatchDev(log2n, src.data_ptr(), dst.data_ptr(), nb, s1, s2, st))
+    print(f"dct{1 << log2n:<2d}: {ms:7.3f} ms  {nb / ms / 1e6:9.2f} G blocks/s  {nsamp * 4 / ms / 1e6:7.0f} GB/s  {nsamp * 4 / ms / 1e6 / 6545.6 * 100:5.1f}% of measured HBM", flush=True)
+line = 1 << 22
+ms = timeit(lambda: xb.xPartialButterfly32Dev(src.data_ptr(), dst.data_ptr(), 4, line, st))
+print(f"partialButterfly32 line={line}: {ms:7.3f} ms  {line * 128 / ms / 1e6:7.0f} GB/s", flush=True)
+n = 1 << 20
+refs = torch.randint(0, 256, (n, 129), device=dev, dtype=torch.uint8)
+modes = (torch.arange(n, device=dev) % 35).to(torch.uint8)
+pred = torch.empty((n, 1024), device=dev, dtype=torch.uint8)
+ms = timeit(lambda: xb.xIntra32PredDev(refs.data_ptr(), modes.data_ptr(), pred.data_ptr(), n, st))
+print(f"intra32 n={n}: {ms:7.3f} ms  {n / ms / 1e6:7.3f} G pred/s  {n * (1024 + 130) / ms / 1e6:7.0f} GB/s  {n * 1154 / ms / 1e6 / 6545.6 * 100:5.1f}% of measured HBM", flush=True)

@@ -147,14 +147,34 @@ def test_bdpi_stream_against_live_reference(x266, ref):
 
 # ------------------------------------------------------------------------------------ DCT N<32
 @pytest.mark.parametrize("log2n", [2, 3, 4])
-@pytest.mark.parametrize("nblk", [1, 3, 64, 1000, 4097])
-def test_dctN(x266, orc, log2n, nblk):
+@pytest.mark.parametrize("nblk", [1, 2, 3, 4, 5, 64, 1000, 4097, 75777])
+@pytest.mark.parametrize("cuda_core", [0, 1])
+def test_dctN(x266, orc, log2n, nblk, cuda_core):
+    """N<32: tensor-core kernels where they exist (tune 3 = 0) and the CUDA-core dctN kernels (tune 3 = 1)"""
     n = 1 << log2n
-    for kind in (0, 2):
-        x = orc.residual(nblk * n * n, 5 + nblk, kind)
+    x266.tune(3, cuda_core)
+    try:
+        for kind in (0, 2):
+            x = orc.residual(nblk * n * n, 5 + nblk, kind)
+            for s1, s2 in (SHIFTS[log2n], (1, 16)):
+                got = x266.xDctNBatch(log2n, x, s1, s2)
+                assert np.array_equal(got, orc.dct(x.reshape(-1, n, n), log2n, s1, s2, threads=4).ravel())
+    finally:
+        x266.tune(3, 0)
+
+
+def test_config4_mixed_partition(x266, orc):
+    """config 4: 3840x2176, every 32x32 region split into 1x32^2 / 4x16^2 / 16x8^2 / 64x4^2 by a
+    seeded draw, blocks gathered per size class, 9-bit residuals, shifts (1,8)/(2,9)/(3,10)/(4,11)."""
+    regions = (3840 // 32) * (2176 // 32)
+    z = np.frombuffer(orc.residual(regions, 268, 2).tobytes(), np.uint16) & 3        # partition class per region
+    for cls, log2n in enumerate((5, 4, 3, 2)):
+        n = 1 << log2n
+        nblk = int((z == cls).sum()) * (1024 // (n * n))
+        x = orc.residual(nblk * n * n, 300 + cls, 0)
         s1, s2 = SHIFTS[log2n]
         got = x266.xDctNBatch(log2n, x, s1, s2)
-        assert np.array_equal(got, orc.dct(x.reshape(-1, n, n), log2n, s1, s2, threads=4).ravel())
+        assert np.array_equal(got, orc.dct(x.reshape(-1, n, n), log2n, s1, s2, threads=8).ravel()), log2n
 
 
 # ---------------------------------------------------------------------------------------- SATD

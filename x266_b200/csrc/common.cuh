@@ -151,6 +151,35 @@ __device__ __forceinline__ void mma_s8s8(int (&d)[4], const uint32_t (&a)[4], ui
           "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
 }
 
+// k16 forms (N<=16 transforms): D(16x8,s32) = A(16x16,s8,row) * B(16x8,{u8|s8},col) + C
+__device__ __forceinline__ void mma16_s8u8(int (&d)[4], const uint32_t (&a)[2], uint32_t b, const int (&c)[4])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+}
+
+__device__ __forceinline__ void mma16_s8s8(int (&d)[4], const uint32_t (&a)[2], uint32_t b, const int (&c)[4])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+}
+
+__device__ __forceinline__ uint2 ld_global_stream_v2(const void* p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void st_global_stream_v2(void* p, uint2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
 // D(16x8,s32) = A(16x32,u8,row) * B(32x8,s8,col) + C   (data on the A side, +-1 Hadamard matrix on the B side)
 __device__ __forceinline__ void mma_u8s8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const int (&c)[4])
 {

@@ -231,9 +231,13 @@ cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int li
     return cudaGetLastError();
 }
 
+static int g_smallCuda = 0;
+void set_small_dct_cuda_cores(int on) { g_smallCuda = on; }
+
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
 {
     if (nBlocks == 0) return cudaSuccess;
+    if (log2n == 4 && !g_smallCuda) return launch_dct16_imma(src, dst, nBlocks, s1, s2, st);
     const size_t nSamples = nBlocks << (2 * log2n);
     const int grid = grid_for((nSamples + 1023) / 1024, DCTN_WARPS, 4);
     switch (log2n) {

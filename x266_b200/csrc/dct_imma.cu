@@ -218,6 +218,118 @@ dct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, si
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 16x16 forward transform on the tensor cores: same choreography as the 32x32 kernel with the k16 MMA
+// (A = G16 is exactly one m16 tile; G16[k][n] = g_t32[2k][n], src_tb/dct32.c:138-143 / mkDct32.bsv).
+// One warp transforms 4 blocks (2 KiB) per iteration; lane (g,q) loads the 8-byte chunk q of rows g and
+// g+8 of each block (bytes t*256 + lane*8: linear, coalesced) and ends with 8 contiguous output bytes per
+// row (sigma16 below), i.e. 256 contiguous bytes per warp store.
+// ------------------------------------------------------------------------------------------------
+constexpr int D16_WARPS = 8;
+
+__device__ __forceinline__ int perm_sigma16(int mu) { return 4 * ((mu >> 1) & 3) + 2 * (mu >> 3) + (mu & 1); }
+// kappa2 = 4q + 2t + e  ->  j = 8t + 2q + e
+__device__ __forceinline__ int perm_pi2_16(int k2) { return 8 * ((k2 >> 1) & 1) + 2 * (k2 >> 2) + (k2 & 1); }
+
+__global__ void __launch_bounds__(D16_WARPS * 32, 2)
+dct16_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    uint32_t A1[2], A2[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int row = g + 8 * r;
+        const int k1 = perm_sigma16(row);
+        A1[r] = pack4(c_g8.v[2 * k1][4 * q + 0], c_g8.v[2 * k1][4 * q + 1], c_g8.v[2 * k1][4 * q + 2], c_g8.v[2 * k1][4 * q + 3]);
+        A2[r] = pack4(c_g8.v[2 * row][perm_pi2_16(4 * q + 0)], c_g8.v[2 * row][perm_pi2_16(4 * q + 1)],
+                      c_g8.v[2 * row][perm_pi2_16(4 * q + 2)], c_g8.v[2 * row][perm_pi2_16(4 * q + 3)]);
+    }
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    const int cAdd1[4] = { add1, add1, add1, add1 };
+    const int cAdd2[4] = { add2, add2, add2, add2 };
+    const int cZero[4] = { 0, 0, 0, 0 };
+
+    const size_t nUnits = (nBlocks + 3) / 4;
+    const size_t first = (size_t)blockIdx.x * D16_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * D16_WARPS;
+
+    auto load_unit = [&](size_t u, uint2 (&w)[4][2]) {
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+            size_t b = u * 4 + bb;
+            b = b < nBlocks ? b : nBlocks - 1;                 // ragged tail: re-read the last block, never stored
+#pragma unroll
+            for (int t = 0; t < 2; t++) w[bb][t] = ld_global_stream_v2(src + b * 256 + t * 128 + lane * 4);
+        }
+    };
+
+    uint2 nxt[4][2] = {};
+    if (first < nUnits) load_unit(first, nxt);
+
+    for (size_t u = first; u < nUnits; u += stride) {
+        uint32_t BL[4][2], BH[4][2];
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++)
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                BL[bb][t] = prmt(nxt[bb][t].x, nxt[bb][t].y, 0x6420);
+                BH[bb][t] = prmt(nxt[bb][t].x, nxt[bb][t].y, 0x7531);
+            }
+        if (u + stride < nUnits) load_unit(u + stride, nxt);
+
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+            int r[2][4];
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                int dl[4], dh[4];
+                mma16_s8u8(dl, A1, BL[bb][t], cAdd1);
+                mma16_s8s8(dh, A1, BH[bb][t], cZero);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r[t][c] = (dl[c] + dh[c] * 256) >> shift1;
+            }
+            uint32_t B2L[2], B2H[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t p0 = prmt(r[0][2 * h], r[0][2 * h + 1], 0x5140);
+                const uint32_t p1 = prmt(r[1][2 * h], r[1][2 * h + 1], 0x5140);
+                B2L[h] = prmt(p0, p1, 0x5410);
+                B2H[h] = prmt(p0, p1, 0x7632);
+            }
+            int r2[2][4];
+#pragma unroll
+            for (int t2 = 0; t2 < 2; t2++) {
+                int dl[4], dh[4];
+                mma16_s8u8(dl, A2, B2L[t2], cAdd2);
+                mma16_s8s8(dh, A2, B2H[t2], cZero);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r2[t2][c] = (dl[c] + dh[c] * 256) >> shift2;
+            }
+            const size_t b = u * 4 + bb;
+            if (b < nBlocks) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint2 o;
+                    o.x = prmt(r2[0][2 * h], r2[0][2 * h + 1], 0x5410);
+                    o.y = prmt(r2[1][2 * h], r2[1][2 * h + 1], 0x5410);
+                    st_global_stream_v2(dst + b * 256 + (g + 8 * h) * 16 + q * 4, o);
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_dct16_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
+{
+    if (nBlocks == 0) return cudaSuccess;
+    const size_t want = ((nBlocks + 3) / 4 + D16_WARPS - 1) / D16_WARPS;
+    const size_t cap = (size_t)sm_count() * 2;
+    dct16_imma_kernel<<<(int)(want < cap ? want : cap), D16_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---- configuration table (index = tuning id).  Shipped default = 6 (8 warps, 2 CTAs/SM, register
 // double-buffered 128-bit global loads): 95.7 % of the measured HBM roofline on B200 vs 86.7 % for the
 // best TMA-ring instantiation (profiles/r01_tune_dct.log).

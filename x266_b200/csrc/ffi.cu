@@ -211,6 +211,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 0) { set_imma_config(value); return 0; }
     if (key == 1) { set_search_v1(value); return 0; }
     if (key == 2) { set_satd_cuda_cores(value); return 0; }
+    if (key == 3) { set_small_dct_cuda_cores(value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }
 

@@ -4,7 +4,7 @@
 // see DESIGN.md):  reference samples left[64] / top[65] (:34-37), per-row index and fraction tables
 // = ((k+1)*angle)>>5 and &31 (:75-112), inverse-angle projection of the side reference for negative
 // angles (:151-220), 2-tap interpolation (:352-368), DC (:388-392).
-// One CTA (256 threads) per prediction, 4 output pixels per thread, 1 KiB coalesced store per CTA.
+// One warp per prediction, 4 output pixels per lane per step, 128-byte coalesced stores.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -15,71 +15,107 @@ __constant__ int c_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, 
 // 8192/|angle| rounded, for angle = -2,-5,-9,-13,-17,-21,-26,-32
 __constant__ int c_intraInv[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
 
-__global__ void __launch_bounds__(256)
+// One warp per prediction.  Lane l produces, for it = 0..7, the 4 pixels (row 4*it + (l>>3), columns
+// 4*(l&7) .. +3) and stores them as one 32-bit word: every warp store is 128 contiguous bytes (4 rows).
+// The reference line ref[-32..65] lives in a per-warp shared-memory strip; VER selects which of
+// (row, column) is the distance from the main reference so that the loop-invariant index/fraction
+// computations are hoisted (per row for vertical modes, per lane for horizontal modes).
+constexpr int INTRA_WARPS = 8;
+constexpr int INTRA_STRIP = 112;            // 32 (negative part) + 66 + padding, multiple of 16
+
+template <bool VER>
+__device__ __forceinline__ void intra_angular(const uint8_t* __restrict__ ref /* -> ref[0] */, int ang, int lane, uint32_t* out)
+{
+    const int rsub = lane >> 3, c0 = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int row = 4 * it + rsub;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int col = c0 + j;
+            const int xr = VER ? col : row;
+            const int yd = VER ? row : col;
+            const int t = (yd + 1) * ang;
+            const int idx = t >> 5, f = t & 31;
+            const int a = ref[xr + idx + 1], b = ref[xr + idx + 2];
+            const int v = ((32 - f) * a + f * b + 16) >> 5;          // f == 0 gives exactly a
+            packed |= (uint32_t)v << (8 * j);
+        }
+        out[it * 32 + lane] = packed;        // word index (4*it + rsub)*8 + (lane&7) == it*32 + lane
+    }
+}
+
+__global__ void __launch_bounds__(INTRA_WARPS * 32)
 intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ modes, uint8_t* __restrict__ pred, size_t n)
 {
-    __shared__ int sref[32 + 65 + 3];       // main reference, index -32..64 at sref[32 + i]
-    __shared__ uint8_t sraw[132];           // left[64] | top[65]
-    __shared__ int sdc;
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) uint8_t strip[INTRA_WARPS][INTRA_STRIP];
+    __shared__ __align__(16) uint8_t raw[INTRA_WARPS][144];      // left[64] | top[65]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sref = strip[warp] + 32;                            // sref[i] = ref[i], i in -32..65
+    uint8_t* sraw = raw[warp];
 
-    for (size_t p = blockIdx.x; p < n; p += gridDim.x) {
-        const int mode = modes[p] > 34 ? 1 : modes[p];   // host API rejects > 34; keep device reads in range
-        if (tid < 129) sraw[tid] = refs[p * 129 + tid];
-        __syncthreads();
+    for (size_t p = (size_t)blockIdx.x * INTRA_WARPS + warp; p < n; p += (size_t)gridDim.x * INTRA_WARPS) {
+        const int mode = modes[p] > 34 ? 1 : modes[p];           // host API rejects > 34; keep device reads in range
+        const uint8_t* src = refs + p * 129;
+#pragma unroll
+        for (int i = lane; i < 129; i += 32) sraw[i] = src[i];
+        __syncwarp();
         const uint8_t* left = sraw;          // left[i] = pixel (-1, i)
         const uint8_t* top = sraw + 64;      // top[0] = corner, top[1+i] = pixel (i, -1)
+        uint32_t* out = reinterpret_cast<uint32_t*>(pred + p * 1024);
         const bool isVer = mode >= 18;
         const int ang = c_intraAngle[mode];
 
         if (mode >= 2) {
-            if (tid <= 64) sref[32 + tid] = isVer ? top[tid] : (tid == 0 ? top[0] : left[tid - 1]);
-            if (ang < 0 && tid >= 1 && tid <= 32 && -tid >= ((32 * ang) >> 5)) {
+#pragma unroll
+            for (int i = lane; i <= 65; i += 32) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
+            if (ang < 0) {
                 int inv = 0;
 #pragma unroll
                 for (int a = 0; a < 8; a++) if (c_intraAngle[11 + a] == ang) inv = c_intraInv[a];
-                const int s = (tid * inv + 128) >> 8;
-                sref[32 - tid] = isVer ? left[s - 1] : top[s];
+                const int k = lane + 1;                           // projects ref[-k], k = 1..32
+                if (-k >= ang) {
+                    const int s = (k * inv + 128) >> 8;
+                    sref[-k] = isVer ? left[s - 1] : top[s];
+                }
             }
-        } else if (mode == 1 && tid < 32) {
-            int s = left[tid] + top[1 + tid];
+            __syncwarp();
+            if (isVer) intra_angular<true>(sref, ang, lane, out);
+            else intra_angular<false>(sref, ang, lane, out);
+        } else if (mode == 1) {
+            int s = left[lane] + top[1 + lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (tid == 0) sdc = (s + 32) >> 6;
-        }
-        __syncthreads();
-
-        const int row = tid >> 3, col0 = (tid & 7) * 4;
-        uint32_t packed = 0;
+            const uint32_t dc = (uint32_t)((s + 32) >> 6) * 0x01010101u;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int col = col0 + i;
-            int v;
-            if (mode == 0) {
-                v = ((31 - col) * left[row] + (col + 1) * top[33] + (31 - row) * top[1 + col] + (row + 1) * left[32] + 32) >> 6;
-            } else if (mode == 1) {
-                v = sdc;
-            } else {
-                const int xr = isVer ? col : row;      // position along the main reference
-                const int yd = isVer ? row : col;      // distance from the main reference
-                const int t = (yd + 1) * ang;
-                const int idx = t >> 5, f = t & 31;
-                const int a = sref[32 + xr + idx + 1];
-                const int b = sref[32 + xr + idx + 2];  // in range: index <= 65 only when f == 0 (slot padded)
-                v = f ? (((32 - f) * a + f * b + 16) >> 5) : a;
+            for (int it = 0; it < 8; it++) out[it * 32 + lane] = dc;
+        } else {
+            const int rsub = lane >> 3, c0 = (lane & 7) * 4;
+            const int tr = top[33], bl = left[32];
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int row = 4 * it + rsub;
+                uint32_t packed = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int col = c0 + j;
+                    const int v = ((31 - col) * left[row] + (col + 1) * tr + (31 - row) * top[1 + col] + (row + 1) * bl + 32) >> 6;
+                    packed |= (uint32_t)v << (8 * j);
+                }
+                out[it * 32 + lane] = packed;
             }
-            packed |= (uint32_t)(v & 0xFF) << (8 * i);
         }
-        reinterpret_cast<uint32_t*>(pred + p * 1024)[tid] = packed;
-        __syncthreads();
+        __syncwarp();
     }
 }
 
 cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    size_t cap = (size_t)sm_count() * 8;
-    intra32_kernel<<<(unsigned)(n < cap ? n : cap), 256, 0, st>>>(refs, mode, pred, n);
+    const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
+    const size_t cap = (size_t)sm_count() * 8;
+    intra32_kernel<<<(unsigned)(want < cap ? want : cap), INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n);
     count_launch();
     return cudaGetLastError();
 }
