@@ -238,6 +238,7 @@ cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlo
 {
     if (nBlocks == 0) return cudaSuccess;
     if (log2n == 4 && !g_smallCuda) return launch_dct16_imma(src, dst, nBlocks, s1, s2, st);
+    if (log2n == 3 && !g_smallCuda) return launch_dct8_imma(src, dst, nBlocks, s1, s2, st);
     const size_t nSamples = nBlocks << (2 * log2n);
     const int grid = grid_for((nSamples + 1023) / 1024, DCTN_WARPS, 4);
     switch (log2n) {

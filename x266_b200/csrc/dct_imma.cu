@@ -330,6 +330,101 @@ cudaError_t launch_dct16_imma(const int16_t* src, int16_t* dst, size_t nBlocks, 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// 8x8 forward transform on the tensor cores: two blocks (alpha, beta) per k16 MMA through the block-
+// diagonal operand diag(G8, G8) (G8[k][n] = g_t32[4k][n], src_tb/dct32.c:132-136).  Rows 0-7 / K 0-7 of the
+// MMA belong to alpha, rows 8-15 / K 8-15 to beta; the 8 columns are the 8 rows j of both blocks.
+// Between the passes each lane owns 2 of the 4 j-values it needs for its K slice, the other 2 sit in lane
+// q^2 of the same quad: one SHFL per block pair.  One warp transforms 16 blocks (2 KiB) per iteration.
+// ------------------------------------------------------------------------------------------------
+constexpr int D8_WARPS = 8;
+
+__global__ void __launch_bounds__(D8_WARPS * 32, 2)
+dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const bool lowHalf = q < 2;                // this lane's K slice belongs to block alpha (else beta)
+    // pass 1: K position 4q+i <-> sample n = 4(q&1)+i of block (q>>1); pass 2: byte i of the K slice <-> j = pi2(i)
+    //   pi2(i) = 2(q&1) + i (i<2),  2(q&1) + 4 + (i-2) (i>=2)
+    uint32_t A1[2], A2[2];
+    {
+        const int n0 = 4 * (q & 1);
+        const uint32_t a1 = pack4(c_g8.v[4 * g][n0 + 0], c_g8.v[4 * g][n0 + 1], c_g8.v[4 * g][n0 + 2], c_g8.v[4 * g][n0 + 3]);
+        const int j0 = 2 * (q & 1);
+        const uint32_t a2 = pack4(c_g8.v[4 * g][j0 + 0], c_g8.v[4 * g][j0 + 1], c_g8.v[4 * g][j0 + 4], c_g8.v[4 * g][j0 + 5]);
+        A1[0] = lowHalf ? a1 : 0u; A1[1] = lowHalf ? 0u : a1;      // a0: row g (alpha rows), a1: row g+8 (beta rows)
+        A2[0] = lowHalf ? a2 : 0u; A2[1] = lowHalf ? 0u : a2;
+    }
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    const int cAdd1[4] = { add1, add1, add1, add1 };
+    const int cAdd2[4] = { add2, add2, add2, add2 };
+    const int cZero[4] = { 0, 0, 0, 0 };
+
+    const size_t nPairs = (nBlocks + 1) / 2;
+    const size_t nUnits = (nPairs + 7) / 8;
+    const size_t first = (size_t)blockIdx.x * D8_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * D8_WARPS;
+    // byte offset of this lane's 8-byte piece inside a 256-byte block pair: block (q>>1), row g, half (q&1)
+    const int laneOff = (q >> 1) * 64 + g * 8 + (q & 1) * 4;        // in int16 units
+
+    auto load_unit = [&](size_t u, uint2 (&w)[8]) {
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            size_t blk = (u * 8 + pp) * 2 + (q >> 1);
+            blk = blk < nBlocks ? blk : nBlocks - 1;               // ragged tail: clamp, never stored
+            w[pp] = ld_global_stream_v2(src + blk * 64 + g * 8 + (q & 1) * 4);
+        }
+    };
+    (void)laneOff;
+
+    uint2 nxt[8] = {};
+    if (first < nUnits) load_unit(first, nxt);
+
+    for (size_t u = first; u < nUnits; u += stride) {
+        uint32_t BL[8], BH[8];
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            BL[pp] = prmt(nxt[pp].x, nxt[pp].y, 0x6420);
+            BH[pp] = prmt(nxt[pp].x, nxt[pp].y, 0x7531);
+        }
+        if (u + stride < nUnits) load_unit(u + stride, nxt);
+
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            int dl[4], dh[4], r[4];
+            mma16_s8u8(dl, A1, BL[pp], cAdd1);
+            mma16_s8s8(dh, A1, BH[pp], cZero);
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] = (dl[c] + dh[c] * 256) >> shift1;
+            // r0,r1: coef_alpha[k=g][j=2q,2q+1];  r2,r3: coef_beta[k=g][j=2q,2q+1]
+            const uint32_t mineA = prmt(r[0], r[1], 0x5410), mineB = prmt(r[2], r[3], 0x5410);
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, lowHalf ? mineB : mineA, 2);
+            const uint32_t firstW = lowHalf ? mineA : recv;         // j = 2(q&1), 2(q&1)+1
+            const uint32_t secondW = lowHalf ? recv : mineB;        // j = 2(q&1)+4, 2(q&1)+5
+            const uint32_t B2L = prmt(firstW, secondW, 0x6420), B2H = prmt(firstW, secondW, 0x7531);
+            mma16_s8u8(dl, A2, B2L, cAdd2);
+            mma16_s8s8(dh, A2, B2H, cZero);
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] = (dl[c] + dh[c] * 256) >> shift2;
+            // r0,r1: dct_alpha[k2=g][k=2q,2q+1];  r2,r3: dct_beta[k2=g][k=2q,2q+1]
+            const size_t b0 = (u * 8 + pp) * 2;
+            if (b0 < nBlocks) *reinterpret_cast<uint32_t*>(dst + b0 * 64 + g * 8 + q * 2) = prmt(r[0], r[1], 0x5410);
+            if (b0 + 1 < nBlocks) *reinterpret_cast<uint32_t*>(dst + (b0 + 1) * 64 + g * 8 + q * 2) = prmt(r[2], r[3], 0x5410);
+        }
+    }
+}
+
+cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
+{
+    if (nBlocks == 0) return cudaSuccess;
+    const size_t want = ((nBlocks + 15) / 16 + D8_WARPS - 1) / D8_WARPS;
+    const size_t cap = (size_t)sm_count() * 2;
+    dct8_imma_kernel<<<(int)(want < cap ? want : cap), D8_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---- configuration table (index = tuning id).  Shipped default = 6 (8 warps, 2 CTAs/SM, register
 // double-buffered 128-bit global loads): 95.7 % of the measured HBM roofline on B200 vs 86.7 % for the
 // best TMA-ring instantiation (profiles/r01_tune_dct.log).

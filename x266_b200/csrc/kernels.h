@@ -12,6 +12,7 @@ void count_launch();            // bumps the library-wide kernel launch counter
 cudaError_t launch_dct32_bfly(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 cudaError_t launch_dct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 cudaError_t launch_dct16_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
+cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 void set_small_dct_cuda_cores(int on);   // tuning/diagnostic: CUDA-core dctN kernels for N=8,16 instead of IMMA
 void set_imma_config(int id);   // tuning/diagnostic: selects a (warps, stages, CTAs/SM, staging) instantiation
 void set_satd_cuda_cores(int on);   // tuning/diagnostic: CUDA-core SATD batch kernel instead of IMMA
