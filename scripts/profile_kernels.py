@@ -16,11 +16,21 @@ for v in (xb.DCT_IMMA, xb.DCT_BFLY):
     xb.set_dct_variant(v)
     for _ in range(3):
         xb.xDct32BatchDev(src.data_ptr(), dst.data_ptr(), n, 6, 11, st)
+for log2n, (s1, s2) in ((2, (1, 8)), (3, (2, 9)), (4, (3, 10))):
+    xb.xDctNBatchDev(log2n, src.data_ptr(), dst.data_ptr(), (n * 1024) >> (2 * log2n), s1, s2, st)
+npred = 1 << 18
+refs = torch.randint(0, 256, (npred, 129), device=dev, dtype=torch.uint8)
+modes = (torch.arange(npred, device=dev) % 35).to(torch.uint8)
+pred = torch.empty((npred, 1024), device=dev, dtype=torch.uint8)
+xb.xIntra32PredDev(refs.data_ptr(), modes.data_ptr(), pred.data_ptr(), npred, st)
 nc = 1 << 22
 d = torch.randint(-255, 256, (nc, 64), device=dev, dtype=torch.int16)
 o = torch.empty(nc, device=dev, dtype=torch.int32)
-for _ in range(3):
-    xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), nc, st)
+for v in (0, 1):
+    xb.tune(2, v)
+    for _ in range(2):
+        xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), nc, st)
+xb.tune(2, 0)
 w, h, rg = 1920, 1080, 32
 cur = torch.randint(0, 256, (h, w), device=dev, dtype=torch.uint8)
 refp = torch.randint(0, 256, (h + 64, w + 64), device=dev, dtype=torch.uint8)
