@@ -120,6 +120,28 @@ int xSatd8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t s
 int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n);
 int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8_t* dPred, size_t n, void* stream);
 
+/* ================================================================================================
+ * "Next" rows: the encoder's tiled frame stores on the device.
+ * A frame is a raster of 512-byte ref_block_t tiles (src/x266.cpp:56-63: m_Y[16*16] | m_C[2*8*8] | m_I[128]),
+ * width/16 tiles per row (m_frames_strd, x266.cpp:503); passed here as void* / uint8_t*.
+ * ============================================================================================== */
+
+/* replaces src/x266.cpp:415-453 (planar YUV 4:2:0 -> tiles; m_I untouched) on device-resident planes */
+int xConvInputFmtDev(void* dTiles, const uint8_t* dY, const uint8_t* dU, const uint8_t* dV, intptr_t strdY,
+                     int width, int height, void* stream);
+/* replaces src/x266.cpp:455-492 (tiles -> planar) */
+int xConvOutput420Dev(const void* dTiles, uint8_t* dY, intptr_t strdY, uint8_t* dU, uint8_t* dV, intptr_t strdC,
+                      int width, int height, void* stream);
+
+/* Fused residual + transform for the block loop of xEncodeFrame (src/x266.cpp:537-546): for every 32x32 luma
+ * block b (raster order, width and height multiples of 32) of the tiled frames cur and pred,
+ *     coef[b] = DCT32(cur_b - pred_b)   with shifts s1/s2 (src_tb/dct32.c:197-198 on the int16 residual).
+ * coef is [nBlocks][32][32] int16, the layout xDct32Batch uses.  The residual is never materialised. */
+int xFrameResiDct32(const void* curTiles, const void* predTiles, int width, int height, int16_t* coef,
+                    int shift1st, int shift2nd);
+int xFrameResiDct32Dev(const void* dCurTiles, const void* dPredTiles, int width, int height, int16_t* dCoef,
+                       int shift1st, int shift2nd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,9 @@ class Oracle:
         L.orc_intra32.argtypes = [_u8p, _u8p, C.c_int, _u8p]
         L.orc_intra_mode_angle.argtypes = [C.c_int]
         L.orc_intra_mode_angle.restype = C.c_int
+        L.orc_conv_input_fmt.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_ssize_t, C.c_int, C.c_int]
+        L.orc_conv_output420.argtypes = [_u8p, _u8p, C.c_ssize_t, _u8p, _u8p, C.c_ssize_t, C.c_int, C.c_int]
+        L.orc_frame_resi_dct32.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _i16p, C.c_int, C.c_int]
         L.orc_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
         L.orc_fnv1a64.restype = C.c_uint64
         L.orc_fill_residual.argtypes = [_i16p, C.c_size_t, C.c_uint64, C.c_int]
@@ -114,6 +117,23 @@ class Oracle:
         pred = np.empty((32, 32), np.uint8)
         self.lib.orc_intra32(np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(top, np.uint8), mode, pred)
         return pred
+
+    # --- tiled frames ----------------------------------------------------------------------
+    def conv_input_fmt(self, Y, U, V):
+        h, w = Y.shape
+        tiles = np.zeros((w // 16) * (h // 16) * 512, np.uint8)
+        self.lib.orc_conv_input_fmt(tiles, np.ascontiguousarray(Y), np.ascontiguousarray(U), np.ascontiguousarray(V), w, w, h)
+        return tiles
+
+    def conv_output420(self, tiles, w, h):
+        Y = np.zeros((h, w), np.uint8); U = np.zeros((h // 2, w // 2), np.uint8); V = np.zeros((h // 2, w // 2), np.uint8)
+        self.lib.orc_conv_output420(np.ascontiguousarray(tiles, np.uint8), Y, w, U, V, w // 2, w, h)
+        return Y, U, V
+
+    def frame_resi_dct32(self, cur_tiles, pred_tiles, w, h, s1, s2):
+        coef = np.zeros((w // 32) * (h // 32) * 1024, np.int16)
+        self.lib.orc_frame_resi_dct32(np.ascontiguousarray(cur_tiles, np.uint8), np.ascontiguousarray(pred_tiles, np.uint8), w, h, coef, s1, s2)
+        return coef.reshape(-1, 32, 32)
 
     # --- KAT helpers -----------------------------------------------------------------------
     def fnv(self, arr):

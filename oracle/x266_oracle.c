@@ -309,6 +309,64 @@ void orc_intra32(const uint8_t left[64], const uint8_t top[65], int mode, uint8_
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Tiled frame format ("next" row N2).  src/x266.cpp:56-63 (ref_block_t: 256 B luma 16x16, 128 B chroma as 8
+ * rows of 8 (U,V) pairs, 128 B info) and src/x266.cpp:415-492 (xConvInputFmt / xConvOutput420): tiles in
+ * raster order, width/16 per row.  Restated per pixel instead of per memcpy row.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_conv_input_fmt(uint8_t* tiles, const uint8_t* Y, const uint8_t* U, const uint8_t* V, intptr_t strdY, int w, int h)
+{
+    const intptr_t strdC = strdY >> 1;
+    const int tpr = w / 16;
+    int x, y;
+    for (y = 0; y < h; y++)
+        for (x = 0; x < w; x++)
+            tiles[((size_t)(y / 16) * tpr + x / 16) * 512 + (y % 16) * 16 + (x % 16)] = Y[y * strdY + x];
+    for (y = 0; y < h / 2; y++)
+        for (x = 0; x < w / 2; x++)
+        {
+            uint8_t* t = tiles + ((size_t)(y / 8) * tpr + x / 8) * 512 + 256 + (y % 8) * 16 + (x % 8) * 2;
+            t[0] = U[y * strdC + x];
+            t[1] = V[y * strdC + x];
+        }
+}
+
+void orc_conv_output420(const uint8_t* tiles, uint8_t* Y, intptr_t strdY, uint8_t* U, uint8_t* V, intptr_t strdC, int w, int h)
+{
+    const int tpr = w / 16;
+    int x, y;
+    for (y = 0; y < h; y++)
+        for (x = 0; x < w; x++)
+            Y[y * strdY + x] = tiles[((size_t)(y / 16) * tpr + x / 16) * 512 + (y % 16) * 16 + (x % 16)];
+    for (y = 0; y < h / 2; y++)
+        for (x = 0; x < w / 2; x++)
+        {
+            const uint8_t* t = tiles + ((size_t)(y / 8) * tpr + x / 8) * 512 + 256 + (y % 8) * 16 + (x % 8) * 2;
+            U[y * strdC + x] = t[0];
+            V[y * strdC + x] = t[1];
+        }
+}
+
+/* luma residual of 32x32 block b (raster) between two tiled frames, then the pinned 2-D transform */
+void orc_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int w, int h, int16_t* coef, int s1, int s2)
+{
+    const int tpr = w / 16, bpr = w / 32;
+    size_t b, nb = (size_t)bpr * (h / 32);
+    for (b = 0; b < nb; b++)
+    {
+        int16_t r[1024];
+        int x, y;
+        const int bx = (int)(b % bpr) * 32, by = (int)(b / bpr) * 32;
+        for (y = 0; y < 32; y++)
+            for (x = 0; x < 32; x++)
+            {
+                const size_t o = ((size_t)((by + y) / 16) * tpr + (bx + x) / 16) * 512 + ((by + y) % 16) * 16 + ((bx + x) % 16);
+                r[y * 32 + x] = (int16_t)((int)cur[o] - (int)pred[o]);
+            }
+        orc_dct2d(r, coef + b * 1024, 5, s1, s2);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * KAT helpers: splitmix64 stream and FNV-1a-64.
  * ---------------------------------------------------------------------------------------------- */
 uint64_t orc_fnv1a64(const void* buf, size_t n)

@@ -29,3 +29,14 @@ modes = (torch.arange(n, device=dev) % 35).to(torch.uint8)
 pred = torch.empty((n, 1024), device=dev, dtype=torch.uint8)
 ms = timeit(lambda: xb.xIntra32PredDev(refs.data_ptr(), modes.data_ptr(), pred.data_ptr(), n, st))
 print(f"intra32 n={n}: {ms:7.3f} ms  {n / ms / 1e6:7.3f} G pred/s  {n * (1024 + 130) / ms / 1e6:7.0f} GB/s  {n * 1154 / ms / 1e6 / 6545.6 * 100:5.1f}% of measured HBM", flush=True)
+# fused residual + DCT32 from tiled frames: one launch over 8 stacked 8K luma frames (7680 x 34816)
+w, h = 7680, 4352 * 8
+ntile = (w // 16) * (h // 16)
+cur = torch.randint(0, 256, (ntile * 512,), device=dev, dtype=torch.uint8)
+prd = torch.randint(0, 256, (ntile * 512,), device=dev, dtype=torch.uint8)
+coef = torch.empty(((w // 32) * (h // 32) * 1024,), device=dev, dtype=torch.int16)
+ms = timeit(lambda: xb.xFrameResiDct32Dev(cur.data_ptr(), prd.data_ptr(), w, h, coef.data_ptr(), 4, 11, st))
+nblk = (w // 32) * (h // 32)
+print(f"frame residual+dct32 (tiled u8 cur/pred -> coef), {nblk} blocks: {ms:7.3f} ms  {nblk / ms / 1e6:6.3f} G blocks/s  "
+      f"{nblk * 4096 / ms / 1e6:7.0f} GB/s useful (2 KB luma in + 2 KB coef out per block; the tiles' chroma/info halves are not touched)  "
+      f"{nblk * 4096 / ms / 1e6 / 6545.6 * 100:5.1f}% of measured HBM", flush=True)

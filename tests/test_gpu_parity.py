@@ -302,3 +302,35 @@ def test_device_pointer_entry_points(x266, orc):
     assert np.array_equal(o.cpu().numpy(), orc.satd(d.cpu().numpy()))
     launches = x266.kernel_launches()
     assert launches > 0
+
+
+# ------------------------------------------------------------------------- tiled frames ("next" N2)
+@pytest.mark.parametrize("w,h", [(32, 32), (96, 64), (1920, 1088)])
+def test_frame_residual_dct32(x266, orc, w, h):
+    """fused residual + DCT32 straight from ref_block_t-tiled frames vs gather + oracle transform"""
+    rng = np.random.default_rng(w)
+    def frame(lo, hi):
+        return orc.conv_input_fmt(rng.integers(lo, hi, (h, w)).astype(np.uint8), rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8),
+                                  rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8))
+    for (a, b) in (((0, 256), (0, 256)), ((255, 256), (0, 1)), ((0, 1), (255, 256))):     # random, +255 flat, -255 flat
+        cur, pred = frame(*a), frame(*b)
+        for sh in ((4, 11), (1, 1)):
+            got = x266.xFrameResiDct32(cur, pred, w, h, *sh)
+            assert np.array_equal(got, orc.frame_resi_dct32(cur, pred, w, h, *sh)), (a, b, sh)
+
+
+def test_conv_input_output_fmt_dev(x266, orc):
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(9)
+    w, h = 176, 144
+    Y, U, V = (rng.integers(0, 256, s).astype(np.uint8) for s in ((h, w), (h // 2, w // 2), (h // 2, w // 2)))
+    dY, dU, dV = (torch.from_numpy(a).to(dev) for a in (Y, U, V))
+    tiles = torch.zeros((w // 16) * (h // 16) * 512, dtype=torch.uint8, device=dev)
+    x266.xConvInputFmtDev(tiles.data_ptr(), dY.data_ptr(), dU.data_ptr(), dV.data_ptr(), w, w, h)
+    torch.cuda.synchronize()
+    assert np.array_equal(tiles.cpu().numpy(), orc.conv_input_fmt(Y, U, V))
+    oY, oU, oV = torch.zeros_like(dY), torch.zeros_like(dU), torch.zeros_like(dV)
+    x266.xConvOutput420Dev(tiles.data_ptr(), oY.data_ptr(), w, oU.data_ptr(), oV.data_ptr(), w // 2, w, h)
+    torch.cuda.synchronize()
+    assert np.array_equal(oY.cpu().numpy(), Y) and np.array_equal(oU.cpu().numpy(), U) and np.array_equal(oV.cpu().numpy(), V)

@@ -182,3 +182,34 @@ def test_imma_kernel_model_matches_oracle(orc):
     for kind, sh in ((0, (4, 11)), (1, (6, 11)), (2, (4, 11)), (2, (1, 16))):
         x = orc.residual(1024, 1000 + kind, kind).reshape(32, 32)
         assert (dct32_imma_model(x, g, *sh) == orc.dct(x.reshape(1, 32, 32), 5, *sh)[0]).all()
+
+
+def test_tiled_frame_format_roundtrip(orc):
+    """xConvInputFmt / xConvOutput420 restatement (src/x266.cpp:415-492): the reference's own (disabled) unit test
+    converts a 32x16 ramp to tiles and back (x266.cpp:614-643); we do that plus a random frame, and check the
+    tile layout literally: m_Y row-major 16x16, m_C rows of (U,V) pairs at byte 256."""
+    rng = np.random.default_rng(2)
+    for w, h in ((32, 16), (64, 48)):
+        Y = (np.arange(w * h) % 251).astype(np.uint8).reshape(h, w) if w == 32 else rng.integers(0, 256, (h, w)).astype(np.uint8)
+        U = rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8)
+        V = rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8)
+        t = orc.conv_input_fmt(Y, U, V).reshape(h // 16, w // 16, 512)
+        assert (t[0, 1, :256].reshape(16, 16) == Y[:16, 16:32]).all()
+        assert (t[0, 1, 256:384].reshape(8, 8, 2)[:, :, 0] == U[:8, 8:16]).all()
+        assert (t[0, 1, 256:384].reshape(8, 8, 2)[:, :, 1] == V[:8, 8:16]).all()
+        assert (t[:, :, 384:] == 0).all()
+        Y2, U2, V2 = orc.conv_output420(t.ravel(), w, h)
+        assert (Y2 == Y).all() and (U2 == U).all() and (V2 == V).all()
+
+
+def test_frame_residual_dct_oracle_composition(orc):
+    rng = np.random.default_rng(3)
+    w, h = 96, 64
+    planes = [rng.integers(0, 256, s).astype(np.uint8) for s in ((h, w), (h // 2, w // 2), (h // 2, w // 2))] 
+    cur = orc.conv_input_fmt(*planes)
+    planes2 = [rng.integers(0, 256, s).astype(np.uint8) for s in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
+    pred = orc.conv_input_fmt(*planes2)
+    got = orc.frame_resi_dct32(cur, pred, w, h, 4, 11)
+    resi = planes[0].astype(np.int16) - planes2[0].astype(np.int16)
+    blocks = resi.reshape(h // 32, 32, w // 32, 32).transpose(0, 2, 1, 3).reshape(-1, 32, 32)
+    assert (got == orc.dct(blocks, 5, 4, 11)).all()

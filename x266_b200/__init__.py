@@ -11,5 +11,6 @@ from .binding import (  # noqa: F401
     partialButterfly32, satd8x8, g_t32,
     xDct32Batch, xDctNBatch, xSatd8x8Batch, xSatd8x8Search, xIntra32Pred,
     xDct32BatchDev, xDctNBatchDev, xSatd8x8BatchDev, xSatd8x8SearchDev, xIntra32PredDev, xPartialButterfly32Dev,
+    xFrameResiDct32, xFrameResiDct32Dev, xConvInputFmtDev, xConvOutput420Dev,
     bdpi_dct_block, bdpi_satd_block, X266Error,
 )

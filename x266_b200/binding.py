@@ -57,6 +57,10 @@ def lib():
     L.xSatd8x8SearchDev.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp]
     L.xIntra32Pred.argtypes = [vp, vp, vp, sz]
     L.xIntra32PredDev.argtypes = [vp, vp, vp, sz, vp]
+    L.xConvInputFmtDev.argtypes = [vp, vp, vp, vp, C.c_ssize_t, i, i, vp]
+    L.xConvOutput420Dev.argtypes = [vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, i, i, vp]
+    L.xFrameResiDct32.argtypes = [vp, vp, i, i, vp, i, i]
+    L.xFrameResiDct32Dev.argtypes = [vp, vp, i, i, vp, i, i, vp]
     L.partialButterfly32.argtypes = [vp, vp, i, i]
     L.partialButterfly32.restype = None
     L.satd8x8.argtypes = [vp]
@@ -162,6 +166,28 @@ def xIntra32Pred(refs, modes):
     pred = np.empty((modes.size, 32, 32), np.uint8)
     _ck(lib().xIntra32Pred(refs.ctypes.data, modes.ctypes.data, pred.ctypes.data, modes.size), "xIntra32Pred")
     return pred
+
+
+def xFrameResiDct32(cur_tiles, pred_tiles, width, height, shift1st=4, shift2nd=11):
+    cur_tiles = _np(cur_tiles, np.uint8)
+    pred_tiles = _np(pred_tiles, np.uint8)
+    assert cur_tiles.size == pred_tiles.size == (width // 16) * (height // 16) * 512
+    coef = np.empty(((width // 32) * (height // 32), 32, 32), np.int16)
+    _ck(lib().xFrameResiDct32(cur_tiles.ctypes.data, pred_tiles.ctypes.data, width, height, coef.ctypes.data, shift1st, shift2nd),
+        "xFrameResiDct32")
+    return coef
+
+
+def xConvInputFmtDev(d_tiles, d_y, d_u, d_v, strd_y, width, height, stream=0):
+    _ck(lib().xConvInputFmtDev(d_tiles, d_y, d_u, d_v, strd_y, width, height, stream), "xConvInputFmtDev")
+
+
+def xConvOutput420Dev(d_tiles, d_y, strd_y, d_u, d_v, strd_c, width, height, stream=0):
+    _ck(lib().xConvOutput420Dev(d_tiles, d_y, strd_y, d_u, d_v, strd_c, width, height, stream), "xConvOutput420Dev")
+
+
+def xFrameResiDct32Dev(d_cur, d_pred, width, height, d_coef, shift1st, shift2nd, stream=0):
+    _ck(lib().xFrameResiDct32Dev(d_cur, d_pred, width, height, d_coef, shift1st, shift2nd, stream), "xFrameResiDct32Dev")
 
 
 # ---- Tier 3, device pointers (ints) --------------------------------------------------------------

@@ -425,6 +425,129 @@ cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, i
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// "Next" row N2/N1: residual formation + 32x32 transform straight from the encoder's tiled
+// frame stores.  Frames are rasters of ref_block_t tiles (src/x266.cpp:56-63: 512 bytes = m_Y[16*16] |
+// m_C[2*8*8] | m_I[128]; stride m_frames_strd = width/16 tiles, x266.cpp:503), written by xConvInputFmt
+// (x266.cpp:415-453).  For every 32x32 luma block (2x2 tiles) of `cur` and `pred`:
+//     coef = DCT32( cur - pred )            (dct32.c:197-198 on the 9-bit residual)
+// Linearity makes the residual free: G*(c - p) = G*c + (-G)*p, both operands are raw u8 pixels, so pass 1
+// is two s8 x u8 MMAs into one accumulator per tile -- no subtraction, no byte-plane split, no combine.
+// Pass 2 and the store are those of dct32_imma_kernel.  The int16 residual never exists in memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int FR_WARPS = 8;
+
+__global__ void __launch_bounds__(FR_WARPS * 32, 2)
+frame_resi_dct32_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ pred, int tilesPerRow, int blocksPerRow,
+                        size_t nBlocks, int16_t* __restrict__ dst, int shift1, int shift2)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    uint32_t A1[2][4], A1n[2][4], A2[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int row = 16 * m + g + 8 * (r & 1);
+            const int kb = 16 * (r >> 1) + 4 * q;
+            const int k1 = perm_sigma(row);
+            const int a = c_g8.v[k1][perm_pi(kb + 0)], b = c_g8.v[k1][perm_pi(kb + 1)];
+            const int c = c_g8.v[k1][perm_pi(kb + 2)], d = c_g8.v[k1][perm_pi(kb + 3)];
+            A1[m][r] = pack4(a, b, c, d);
+            A1n[m][r] = pack4(-a, -b, -c, -d);
+            A2[m][r] = pack4(c_g8.v[row][perm_pi2(kb + 0)], c_g8.v[row][perm_pi2(kb + 1)],
+                             c_g8.v[row][perm_pi2(kb + 2)], c_g8.v[row][perm_pi2(kb + 3)]);
+        }
+    }
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    const int cAdd1[4] = { add1, add1, add1, add1 };
+    const int cAdd2[4] = { add2, add2, add2, add2 };
+    const int cZero[4] = { 0, 0, 0, 0 };
+
+    const size_t first = (size_t)blockIdx.x * FR_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * FR_WARPS;
+
+    // lane's 8 pixels of row j = 8t+g: columns 8q..8q+7 -> tile column q>>1, in-tile offset (j&15)*16 + 8*(q&1)
+    auto load_block = [&](size_t b, uint2 (&c)[4], uint2 (&p)[4]) {
+        const size_t by = b / blocksPerRow, bx = b - by * blocksPerRow;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int j = 8 * t + g;
+            const size_t tile = (2 * by + (j >> 4)) * tilesPerRow + 2 * bx + (q >> 1);
+            const size_t off = tile * 512 + (j & 15) * 16 + 8 * (q & 1);
+            c[t] = ld_global_stream_v2(cur + off);
+            p[t] = ld_global_stream_v2(pred + off);
+        }
+    };
+
+    uint2 nc[4] = {}, np[4] = {};
+    if (first < nBlocks) load_block(first, nc, np);
+
+    for (size_t b = first; b < nBlocks; b += stride) {
+        uint2 bc[4], bp[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { bc[t] = nc[t]; bp[t] = np[t]; }
+        if (b + stride < nBlocks) load_block(b + stride, nc, np);
+
+        uint32_t B2L[4][2], B2H[4][2];
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            int r[4][4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int acc[4];
+                mma_s8u8(acc, A1[m], bc[t].x, bc[t].y, cAdd1);
+                mma_s8u8(acc, A1n[m], bp[t].x, bp[t].y, acc);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r[t][c] = acc[c] >> shift1;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t p0 = prmt(r[0][2 * h], r[0][2 * h + 1], 0x5140);
+                const uint32_t p1 = prmt(r[1][2 * h], r[1][2 * h + 1], 0x5140);
+                const uint32_t p2 = prmt(r[2][2 * h], r[2][2 * h + 1], 0x5140);
+                const uint32_t p3 = prmt(r[3][2 * h], r[3][2 * h + 1], 0x5140);
+                B2L[2 * m + h][0] = prmt(p0, p1, 0x5410); B2H[2 * m + h][0] = prmt(p0, p1, 0x7632);
+                B2L[2 * m + h][1] = prmt(p2, p3, 0x5410); B2H[2 * m + h][1] = prmt(p2, p3, 0x7632);
+            }
+        }
+        int16_t* d = dst + b * 1024;
+#pragma unroll
+        for (int m2 = 0; m2 < 2; m2++) {
+            int r[4][4];
+#pragma unroll
+            for (int t2 = 0; t2 < 4; t2++) {
+                int dl[4], dh[4];
+                mma_s8u8(dl, A2[m2], B2L[t2][0], B2L[t2][1], cAdd2);
+                mma_s8s8(dh, A2[m2], B2H[t2][0], B2H[t2][1], cZero);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r[t2][c] = (dl[c] + dh[c] * 256) >> shift2;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint4 o;
+                o.x = prmt(r[0][2 * h], r[0][2 * h + 1], 0x5410);
+                o.y = prmt(r[1][2 * h], r[1][2 * h + 1], 0x5410);
+                o.z = prmt(r[2][2 * h], r[2][2 * h + 1], 0x5410);
+                o.w = prmt(r[3][2 * h], r[3][2 * h + 1], 0x5410);
+                st_global_stream(d + (16 * m2 + 8 * h + g) * 32 + q * 8, o);
+            }
+        }
+    }
+}
+
+cudaError_t launch_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int width, int height, int16_t* dst,
+                                    int s1, int s2, cudaStream_t st)
+{
+    if (width <= 0 || height <= 0 || (width & 31) || (height & 31)) return cudaErrorInvalidValue;
+    const size_t nBlocks = (size_t)(width / 32) * (height / 32);
+    const size_t want = (nBlocks + FR_WARPS - 1) / FR_WARPS;
+    const size_t cap = (size_t)sm_count() * 2;
+    frame_resi_dct32_kernel<<<(int)(want < cap ? want : cap), FR_WARPS * 32, 0, st>>>(cur, pred, width / 16, width / 32, nBlocks, dst, s1, s2);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---- configuration table (index = tuning id).  Shipped default = 6 (8 warps, 2 CTAs/SM, register
 // double-buffered 128-bit global loads): 95.7 % of the measured HBM roofline on B200 vs 86.7 % for the
 // best TMA-ring instantiation (profiles/r01_tune_dct.log).

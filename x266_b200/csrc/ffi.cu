@@ -369,6 +369,57 @@ extern "C" int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* p
     return 0;
 }
 
+// ---- "next" rows: the encoder's tiled frame format on the device ---------------------------------------
+extern "C" int xConvInputFmtDev(void* dTiles, const uint8_t* dY, const uint8_t* dU, const uint8_t* dV, intptr_t strdY,
+                                int width, int height, void* stream)
+{
+    // replaces src/x266.cpp:415-453 on device-resident planes
+    if (!dTiles || !dY || !dU || !dV || strdY < width || (reinterpret_cast<uintptr_t>(dTiles) & 15)) return fail("xConvInputFmtDev", cudaSuccess);
+    CK(launch_conv_input_fmt((uint8_t*)dTiles, dY, dU, dV, strdY, width, height, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xConvOutput420Dev(const void* dTiles, uint8_t* dY, intptr_t strdY, uint8_t* dU, uint8_t* dV, intptr_t strdC,
+                                 int width, int height, void* stream)
+{
+    // replaces src/x266.cpp:455-492
+    if (!dTiles || !dY || !dU || !dV || strdY < width || strdC < width / 2 || (reinterpret_cast<uintptr_t>(dTiles) & 15))
+        return fail("xConvOutput420Dev", cudaSuccess);
+    CK(launch_conv_output420((const uint8_t*)dTiles, dY, strdY, dU, dV, strdC, width, height, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xFrameResiDct32Dev(const void* dCurTiles, const void* dPredTiles, int width, int height, int16_t* dCoef,
+                                  int s1, int s2, void* stream)
+{
+    if (!dCurTiles || !dPredTiles || !dCoef || !shifts_ok(s1, s2)) return fail("xFrameResiDct32Dev", cudaSuccess);
+    if ((reinterpret_cast<uintptr_t>(dCurTiles) | reinterpret_cast<uintptr_t>(dPredTiles) | reinterpret_cast<uintptr_t>(dCoef)) & 15)
+        return fail("xFrameResiDct32Dev: 16-byte alignment", cudaSuccess);
+    CK(launch_frame_resi_dct32((const uint8_t*)dCurTiles, (const uint8_t*)dPredTiles, width, height, dCoef, s1, s2, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xFrameResiDct32(const void* curTiles, const void* predTiles, int width, int height, int16_t* coef, int s1, int s2)
+{
+    if (!curTiles || !predTiles || !coef || !shifts_ok(s1, s2) || width <= 0 || height <= 0 || (width & 31) || (height & 31))
+        return fail("xFrameResiDct32", cudaSuccess);
+    Ctx* c;
+    if (ctx_get(&c)) return -1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t tileBytes = (size_t)(width / 16) * (height / 16) * 512;
+    const size_t coefBytes = (size_t)width * height * 2;
+    if (ensure(&c->dAux, &c->capAux, 2 * tileBytes)) return -1;
+    if (ensure(&c->dOut[0], &c->capOut[0], coefBytes)) return -1;
+    uint8_t* dCur = (uint8_t*)c->dAux;
+    uint8_t* dPred = dCur + tileBytes;
+    CK(cudaMemcpyAsync(dCur, curTiles, tileBytes, cudaMemcpyHostToDevice, c->st[0]));
+    CK(cudaMemcpyAsync(dPred, predTiles, tileBytes, cudaMemcpyHostToDevice, c->st[0]));
+    CK(launch_frame_resi_dct32(dCur, dPred, width, height, (int16_t*)c->dOut[0], s1, s2, c->st[0]));
+    CK(cudaMemcpyAsync(coef, c->dOut[0], coefBytes, cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return 0;
+}
+
 // ================================================================================================
 // Tier 2 (reference signatures; host pointers; synchronous)
 // ================================================================================================

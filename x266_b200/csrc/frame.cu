@@ -1,0 +1,91 @@
+// frame.cu -- the encoder's frame <-> tile format on the device ("next" row N2).
+// Reference behaviour: src/x266.cpp:415-453 (xConvInputFmt: planar YUV 4:2:0 -> raster of 512-byte
+// ref_block_t tiles, m_Y[16*16] | m_C[8 rows x (U,V) x 8] | m_I[128]) and src/x266.cpp:455-492
+// (xConvOutput420, the inverse).  One thread per 16 output bytes, fully coalesced on the tile side.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace x266 {
+
+__global__ void __launch_bounds__(256)
+conv_input_fmt_kernel(uint8_t* __restrict__ tiles, const uint8_t* __restrict__ Y, const uint8_t* __restrict__ U,
+                      const uint8_t* __restrict__ V, intptr_t strdY, int tilesPerRow, size_t nTiles)
+{
+    // 24 16-byte pieces per tile: 16 luma rows + 8 interleaved chroma rows (m_I is left untouched)
+    const intptr_t strdC = strdY >> 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nTiles * 24; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t tile = i / 24;
+        const int piece = (int)(i - tile * 24);
+        const size_t ty = tile / tilesPerRow, tx = tile - ty * tilesPerRow;
+        uint8_t* dst = tiles + tile * 512 + piece * 16;
+        uint8_t v[16];
+        if (piece < 16) {
+            const uint8_t* s = Y + (ty * 16 + piece) * strdY + tx * 16;
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = s[k];
+        } else {
+            const int r = piece - 16;
+            const uint8_t* su = U + (ty * 8 + r) * strdC + tx * 8;
+            const uint8_t* sv = V + (ty * 8 + r) * strdC + tx * 8;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[2 * k] = su[k]; v[2 * k + 1] = sv[k]; }
+        }
+        uint4 o;
+        o.x = v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24);
+        o.y = v[4] | (v[5] << 8) | (v[6] << 16) | ((uint32_t)v[7] << 24);
+        o.z = v[8] | (v[9] << 8) | (v[10] << 16) | ((uint32_t)v[11] << 24);
+        o.w = v[12] | (v[13] << 8) | (v[14] << 16) | ((uint32_t)v[15] << 24);
+        *reinterpret_cast<uint4*>(dst) = o;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+conv_output420_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ Y, intptr_t strdY, uint8_t* __restrict__ U,
+                      uint8_t* __restrict__ V, intptr_t strdC, int tilesPerRow, size_t nTiles)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nTiles * 24; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t tile = i / 24;
+        const int piece = (int)(i - tile * 24);
+        const size_t ty = tile / tilesPerRow, tx = tile - ty * tilesPerRow;
+        const uint4 w = *reinterpret_cast<const uint4*>(tiles + tile * 512 + piece * 16);
+        const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+        if (piece < 16) {
+            uint8_t* d = Y + (ty * 16 + piece) * strdY + tx * 16;
+#pragma unroll
+            for (int k = 0; k < 16; k++) d[k] = (uint8_t)(ww[k >> 2] >> (8 * (k & 3)));
+        } else {
+            const int r = piece - 16;
+            uint8_t* du = U + (ty * 8 + r) * strdC + tx * 8;
+            uint8_t* dv = V + (ty * 8 + r) * strdC + tx * 8;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                du[k] = (uint8_t)(ww[k >> 1] >> (16 * (k & 1)));
+                dv[k] = (uint8_t)(ww[k >> 1] >> (16 * (k & 1) + 8));
+            }
+        }
+    }
+}
+
+cudaError_t launch_conv_input_fmt(uint8_t* tiles, const uint8_t* Y, const uint8_t* U, const uint8_t* V, intptr_t strdY,
+                                  int width, int height, cudaStream_t st)
+{
+    if (width <= 0 || height <= 0 || (width & 15) || (height & 15)) return cudaErrorInvalidValue;
+    const size_t nTiles = (size_t)(width / 16) * (height / 16);
+    const size_t want = (nTiles * 24 + 255) / 256, cap = (size_t)sm_count() * 8;
+    conv_input_fmt_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(tiles, Y, U, V, strdY, width / 16, nTiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_output420(const uint8_t* tiles, uint8_t* Y, intptr_t strdY, uint8_t* U, uint8_t* V, intptr_t strdC,
+                                  int width, int height, cudaStream_t st)
+{
+    if (width <= 0 || height <= 0 || (width & 15) || (height & 15)) return cudaErrorInvalidValue;
+    const size_t nTiles = (size_t)(width / 16) * (height / 16);
+    const size_t want = (nTiles * 24 + 255) / 256, cap = (size_t)sm_count() * 8;
+    conv_output420_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(tiles, Y, strdY, U, V, strdC, width / 16, nTiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace x266

@@ -20,6 +20,12 @@ void set_search_v1(int on);     // tuning/diagnostic: force the v1 (one CTA per 
 cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int line, cudaStream_t st);
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 
+cudaError_t launch_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int width, int height, int16_t* dst,
+                                    int s1, int s2, cudaStream_t st);
+cudaError_t launch_conv_input_fmt(uint8_t* tiles, const uint8_t* Y, const uint8_t* U, const uint8_t* V, intptr_t strdY,
+                                  int width, int height, cudaStream_t st);
+cudaError_t launch_conv_output420(const uint8_t* tiles, uint8_t* Y, intptr_t strdY, uint8_t* U, uint8_t* V, intptr_t strdC,
+                                  int width, int height, cudaStream_t st);
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st);
 cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                   size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
