@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Small invocation of every kernel (all variants) for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import x266_b200 as xb
+from oracle import Oracle
+o = Oracle()
+ok = True
+def check(name, cond):
+    global ok
+    print(("ok   " if cond else "FAIL ") + name, flush=True)
+    ok = ok and bool(cond)
+x = o.residual(301 * 1024, 1, 2)
+want = o.dct(x.reshape(-1, 32, 32), 5, 4, 11, threads=4).ravel()
+for v, name in ((xb.DCT_BFLY, "bfly"), (xb.DCT_IMMA, "imma direct")):
+    xb.set_dct_variant(v)
+    check("dct32 " + name, np.array_equal(xb.xDct32Batch(x, 4, 11), want))
+xb.set_dct_variant(xb.DCT_IMMA)
+for cfg in (0, 2, 5, 13):
+    xb.tune(0, cfg)
+    check(f"dct32 imma cfg {cfg}", np.array_equal(xb.xDct32Batch(x, 4, 11), want))
+xb.tune(0, -1); xb.set_dct_variant(xb.DCT_AUTO)
+for log2n, sh in ((2, (1, 8)), (3, (2, 9)), (4, (3, 10))):
+    n = 1 << log2n
+    xs = o.residual(1237 * n * n, 2, 2)
+    for cc in (0, 1):
+        xb.tune(3, cc)
+        check(f"dct{n} cuda_core={cc}", np.array_equal(xb.xDctNBatch(log2n, xs, *sh), o.dct(xs.reshape(-1, n, n), log2n, *sh).ravel()))
+xb.tune(3, 0)
+check("partialButterfly32", np.array_equal(xb.partialButterfly32(x[:77 * 32], 4, 77), o.partial(x[:77 * 32], 4, 77)))
+d = o.residual(1003 * 64, 3, 2)
+for v in (0, 1):
+    xb.tune(2, v)
+    check(f"satd batch cuda_core={v}", np.array_equal(xb.xSatd8x8Batch(d), o.satd(d)))
+xb.tune(2, 0)
+rng = np.random.default_rng(0)
+for R, (w, h) in ((3, (40, 24)), (8, (200, 24)), (32, (200, 16))):
+    cur = rng.integers(0, 256, (h, w)).astype(np.uint8)
+    refp = rng.integers(0, 256, (h + 2 * R, w + 2 * R)).astype(np.uint8)
+    wc, wb = o.satd_search(cur, refp, R, 0, (w // 8) * (h // 8))
+    for v1 in (0, 1, 2):
+        xb.tune(1, v1)
+        c, b = xb.xSatd8x8Search(cur, refp, R)
+        check(f"search R={R} mode={v1}", np.array_equal(c, wc) and np.array_equal(b, wb))
+xb.tune(1, 0)
+refs = rng.integers(0, 256, (70, 129)).astype(np.uint8)
+modes = np.tile(np.arange(35, dtype=np.uint8), 2)
+pred = xb.xIntra32Pred(refs, modes)
+check("intra32", all(np.array_equal(pred[i], o.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))) for i in range(70)))
+w, h = 96, 64
+fr = lambda: o.conv_input_fmt(rng.integers(0, 256, (h, w)).astype(np.uint8), rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8), rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8))
+a, b = fr(), fr()
+check("frame resi dct32", np.array_equal(xb.xFrameResiDct32(a, b, w, h, 4, 11), o.frame_resi_dct32(a, b, w, h, 4, 11)))
+print("ALL OK" if ok else "SOME FAILED")
+sys.exit(0 if ok else 1)

@@ -359,7 +359,8 @@ satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     constexpr int SIDE = 2 * R + 1;
     constexpr int WS = 2 * R + 8;
     constexpr int SLOTS = R / 4 + 1;
-    __shared__ uint8_t win[WS][COLS + 8];
+    constexpr int WROW = NT + 8;                 // every lane of the last warp may touch column 32*(NW-1)+38
+    __shared__ uint8_t win[WS][WROW];
     __shared__ int V[NW][8][S2_VW];
     __shared__ __align__(16) int tcur[S2_NB][S2_TC_STRIDE];
     __shared__ unsigned long long sBest[S2_NB];
@@ -375,8 +376,8 @@ satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     const int nPos = 8 * (nb - 1) + 2 * R + 1;
 
     const uint8_t* wsrc = refPad + (intptr_t)by * strd + bx0;
-    for (int idx = tid; idx < WS * (COLS + 8); idx += NT) {
-        const int yy = idx / (COLS + 8), xx = idx - yy * (COLS + 8);
+    for (int idx = tid; idx < WS * WROW; idx += NT) {
+        const int yy = idx / WROW, xx = idx - yy * WROW;
         win[yy][xx] = xx < cols ? wsrc[(intptr_t)yy * strd + xx] : (uint8_t)0;
     }
     if (tid < S2_NB) sBest[tid] = ~0ull;
