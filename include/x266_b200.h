@@ -114,6 +114,15 @@ int xSatd8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, 
 int xSatd8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
                       size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream);
 
+/* Plain SAD ("next" row N4).  sad() keeps the reference's name and signature
+ * (riscv/programs/benchmarks/sad/sad.c:27-38: sum |a-b| over an n x n byte region; host pointers, synchronous).
+ * xSad8x8Search is the integer-pel pre-filter with exactly the conventions of xSatd8x8Search (cost = SAD). */
+int sad(unsigned char* input_data1, unsigned char* input_data2, size_t n);
+int xSad8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                  size_t blk0, size_t blk1, uint32_t* cost, int32_t* best);
+int xSad8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                     size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream);
+
 /* 32x32 intra prediction (src/mkIntra32-wip.bsv:34-48,61-397): n predictions; refs[i] = 64 left
  * pixels then 65 top pixels (corner first) = 129 bytes; mode[i] in 0..34 (0 planar, 1 DC, 2..34
  * angular); pred[i] = 32x32 u8 row-major. */

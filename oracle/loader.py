@@ -49,6 +49,8 @@ class Oracle:
         L.orc_satd_search_block.argtypes = [_u8p, C.c_int, _u8p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, _u32p]
         L.orc_satd_search_frame.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_ssize_t, C.c_int, C.c_size_t,
                                             C.c_size_t, C.c_void_p, C.c_void_p]
+        L.orc_sad_search_frame.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_ssize_t, C.c_int, C.c_size_t,
+                                           C.c_size_t, C.c_void_p, C.c_void_p]
         L.orc_sad.argtypes = [_u8p, C.c_ssize_t, _u8p, C.c_ssize_t, C.c_int, C.c_int]
         L.orc_sad.restype = C.c_uint32
         L.orc_intra32.argtypes = [_u8p, _u8p, C.c_int, _u8p]
@@ -105,6 +107,14 @@ class Oracle:
         self.lib.orc_satd_search_frame(cur, w, h, ref_pad, ref_pad.shape[1], rng, blk0, blk1,
                                        cost.ctypes.data if want_cost else None,
                                        best.ctypes.data if want_best else None)
+        return cost, best
+
+    def sad_search(self, cur, ref_pad, rng, blk0, blk1):
+        cur = np.ascontiguousarray(cur, np.uint8); ref_pad = np.ascontiguousarray(ref_pad, np.uint8)
+        h, w = cur.shape
+        side = 2 * rng + 1
+        cost = np.empty((blk1 - blk0, side, side), np.uint32); best = np.empty((blk1 - blk0, 3), np.int32)
+        self.lib.orc_sad_search_frame(cur, w, h, ref_pad, ref_pad.shape[1], rng, blk0, blk1, cost.ctypes.data, best.ctypes.data)
         return cost, best
 
     def sad(self, a, b):

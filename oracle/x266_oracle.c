@@ -235,6 +235,33 @@ uint32_t orc_sad(const uint8_t* a, intptr_t sa, const uint8_t* b, intptr_t sb, i
     return s;
 }
 
+/* SAD full search: same window / argmin conventions as the SATD search, cost = orc_sad of the 8x8 block pair. */
+void orc_sad_search_frame(const uint8_t* cur, int w, int h, const uint8_t* refPad, intptr_t strd,
+                          int range, size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
+{
+    const int bw = w / 8, side = 2 * range + 1;
+    uint32_t* tmp = (uint32_t*)malloc((size_t)side * side * sizeof(uint32_t));
+    size_t b;
+    (void)h;
+    for (b = blk0; b < blk1; b++)
+    {
+        const int bx = (int)(b % bw) * 8, by = (int)(b / bw) * 8;
+        uint32_t* c = cost ? cost + (b - blk0) * side * side : tmp;
+        int mvx, mvy;
+        for (mvy = -range; mvy <= range; mvy++)
+            for (mvx = -range; mvx <= range; mvx++)
+                c[(mvy + range) * side + mvx + range] =
+                    orc_sad(cur + (size_t)by * w + bx, w, refPad + (intptr_t)(by + mvy + range) * strd + bx + mvx + range, strd, 8, 8);
+        if (best)
+        {
+            uint32_t bc; int mx, my;
+            orc_satd_argmin(c, range, &bc, &mx, &my);
+            best[(b - blk0) * 3 + 0] = (int32_t)bc; best[(b - blk0) * 3 + 1] = mx; best[(b - blk0) * 3 + 2] = my;
+        }
+    }
+    free(tmp);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * A6. 32x32 intra prediction, 35 modes (0 planar, 1 DC, 2..34 angular; 10 = horizontal, 26 =
  * vertical).  PARITY UNPINNED (see header).  Spec source: src/mkIntra32-wip.bsv

@@ -29,3 +29,15 @@ for v1 in (1, 0, 2):
         if with_cost: outs[v1] = (cost.clone(), best.clone())
 print("v1 == v2:", torch.equal(outs[0][0], outs[1][0]), torch.equal(outs[0][1], outs[1][1]))
 xb.tune(1, 0)
+# plain SAD full search (N4)
+for with_cost in (True, False):
+    c = cost.data_ptr() if with_cost else 0
+    for _ in range(2):
+        xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c, best.data_ptr(), st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c, best.data_ptr(), st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"SAD search cost_surface={with_cost}: {ms:.3f} ms/frame  {nb*4225/ms/1e6:.1f} G cand/s", flush=True)

@@ -90,6 +90,12 @@ def main():
 
     json.dump(dict(mapTbl=table("mapTbl"), facTbl=table("facTbl"), mapShift=table("mapShift")),
               open(os.path.join(HERE, "intra_tables.json"), "w"))
+    # the reference's own SAD golden dataset (riscv/programs/benchmarks/sad/dataset1.h: two 64x64 inputs + verify_data)
+    ds = open(os.path.join(REF_TREE, "riscv", "programs", "benchmarks", "sad", "dataset1.h")).read()
+    arrs = re.findall(r"(input_data1|input_data2|verify_data)\[DATA_SIZE\]\s*=\s*\{(.*?)\};", ds, re.S)
+    got = {name: np.array([int(v) for v in re.findall(r"-?\d+", body)]) for name, body in arrs}
+    np.savez_compressed(os.path.join(HERE, "sad_dataset.npz"), a=got["input_data1"].astype(np.uint8),
+                        b=got["input_data2"].astype(np.uint8), verify=got["verify_data"][:1].astype(np.int64))
     print("golden written:", sorted(os.listdir(HERE)))
 
 

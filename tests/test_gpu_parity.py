@@ -334,3 +334,30 @@ def test_conv_input_output_fmt_dev(x266, orc):
     x266.xConvOutput420Dev(tiles.data_ptr(), oY.data_ptr(), w, oU.data_ptr(), oV.data_ptr(), w // 2, w, h)
     torch.cuda.synchronize()
     assert np.array_equal(oY.cpu().numpy(), Y) and np.array_equal(oU.cpu().numpy(), U) and np.array_equal(oV.cpu().numpy(), V)
+
+
+# --------------------------------------------------------------------------------- SAD ("next" N4)
+def test_sad_reference_golden_dataset(x266):
+    import os
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "sad_dataset.npz"))
+    assert x266.sad(d["a"], d["b"]) == 344807             # riscv/programs/benchmarks/sad/dataset1.h:423-426
+
+
+@pytest.mark.parametrize("n", [1, 3, 64, 65, 1000])
+def test_sad_region_sizes(x266, orc, n):
+    r = np.random.default_rng(n)
+    a, b = r.integers(0, 256, (n, n)).astype(np.uint8), r.integers(0, 256, (n, n)).astype(np.uint8)
+    assert x266.sad(a, b) == orc.sad(a, b)
+    assert x266.sad(a, a) == 0
+    assert x266.sad(np.zeros((n, n), np.uint8), np.full((n, n), 255, np.uint8)) == 255 * n * n
+
+
+@pytest.mark.parametrize("rng_px", [0, 3, 8, 32])
+def test_sad_search(x266, orc, rng_px):
+    cur, refp = make_frames(72, 40, rng_px, seed=7)
+    cost, best = x266.xSad8x8Search(cur, refp, rng_px)
+    wc, wb = orc.sad_search(cur, refp, rng_px, 0, 45)
+    assert np.array_equal(cost, wc) and np.array_equal(best, wb)
+    c, b = x266.xSad8x8Search(cur, refp, rng_px, 7, 20)
+    assert np.array_equal(c, wc[7:20]) and np.array_equal(b, wb[7:20])

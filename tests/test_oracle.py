@@ -134,6 +134,13 @@ def test_satd_search_oracle_is_satd_of_differences(orc):
         assert best[b].tolist() == [k[0], k[3] - r, k[2] - r]
 
 
+def test_sad_reference_golden_dataset(orc):
+    """the reference's own golden vector for the SAD kernel: 64x64 dataset -> 344807 (sad/dataset1.h:423-426)"""
+    d = np.load(os.path.join(GOLDEN, "sad_dataset.npz"))
+    assert int(d["verify"][0]) == 344807
+    assert orc.sad(d["a"].reshape(64, 64), d["b"].reshape(64, 64)) == 344807
+
+
 def test_sad_matches_riscv_benchmark_definition(orc):
     a = np.arange(64 * 64, dtype=np.uint32).reshape(64, 64).astype(np.uint8)
     b = a[::-1].copy()

@@ -61,6 +61,10 @@ def lib():
     L.xConvOutput420Dev.argtypes = [vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, i, i, vp]
     L.xFrameResiDct32.argtypes = [vp, vp, i, i, vp, i, i]
     L.xFrameResiDct32Dev.argtypes = [vp, vp, i, i, vp, i, i, vp]
+    L.sad.argtypes = [vp, vp, sz]
+    L.sad.restype = i
+    L.xSad8x8Search.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp]
+    L.xSad8x8SearchDev.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp]
     L.partialButterfly32.argtypes = [vp, vp, i, i]
     L.partialButterfly32.restype = None
     L.satd8x8.argtypes = [vp]
@@ -157,6 +161,33 @@ def xSatd8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want
                              cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None),
         "xSatd8x8Search")
     return cost, best
+
+
+def sad(a, b):
+    """reference name/signature: int sad(type* a, type* b, size_t n) over an n x n byte region"""
+    a = _np(a, np.uint8); b = _np(b, np.uint8)
+    n = int(round(a.size ** 0.5))
+    assert n * n == a.size == b.size
+    return int(lib().sad(a.ctypes.data, b.ctypes.data, n))
+
+
+def xSad8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want_best=True):
+    cur = _np(cur, np.uint8); ref_padded = _np(ref_padded, np.uint8)
+    h, w = cur.shape
+    assert ref_padded.shape == (h + 2 * rng, w + 2 * rng)
+    if blk1 is None:
+        blk1 = (w // 8) * (h // 8)
+    side = 2 * rng + 1
+    nb = blk1 - blk0
+    cost = np.empty((nb, side, side), np.uint32) if want_cost else None
+    best = np.empty((nb, 3), np.int32) if want_best else None
+    _ck(lib().xSad8x8Search(cur.ctypes.data, ref_padded.ctypes.data, ref_padded.shape[1], w, h, rng, blk0, blk1,
+                            cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None), "xSad8x8Search")
+    return cost, best
+
+
+def xSad8x8SearchDev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSad8x8SearchDev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream), "xSad8x8SearchDev")
 
 
 def xIntra32Pred(refs, modes):

@@ -293,8 +293,56 @@ extern "C" int xSatd8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded,
     return 0;
 }
 
+typedef cudaError_t (*search_launch_t)(const uint8_t*, const uint8_t*, intptr_t, int, int, int, size_t, size_t, uint32_t*, int32_t*, cudaStream_t);
+static int search_host(search_launch_t launch, const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                       size_t blk0, size_t blk1, uint32_t* cost, int32_t* best);
+
 extern "C" int xSatd8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
                               size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
+{
+    return search_host(launch_satd8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
+}
+
+extern "C" int xSad8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                             size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
+{
+    return search_host(launch_sad8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
+}
+
+extern "C" int xSad8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                                size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
+{
+    if (!dCur || !dRefPadded || w <= 0 || h <= 0 || strd < w + 2 * range) return fail("xSad8x8SearchDev", cudaSuccess);
+    CK(launch_sad8x8_search(dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int sad(unsigned char* input_data1, unsigned char* input_data2, size_t n)
+{
+    // replaces riscv/programs/benchmarks/sad/sad.c:27-38 (host pointers, synchronous)
+    Ctx* c;
+    if (ctx_get(&c)) die("sad");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t bytes = n * n;
+    unsigned out = 0;
+    auto body = [&]() -> int {
+        if (ensure(&c->dIn[0], &c->capIn[0], 2 * bytes + 256)) return -1;
+        if (ensure(&c->dOut[0], &c->capOut[0], 256)) return -1;
+        uint8_t* dA = (uint8_t*)c->dIn[0];
+        uint8_t* dB = dA + ((bytes + 255) & ~(size_t)255);
+        CK(cudaMemcpyAsync(dA, input_data1, bytes, cudaMemcpyHostToDevice, c->st[0]));
+        CK(cudaMemcpyAsync(dB, input_data2, bytes, cudaMemcpyHostToDevice, c->st[0]));
+        CK(launch_sad_region(dA, dB, bytes, (unsigned*)c->dOut[0], c->st[0]));
+        CK(cudaMemcpyAsync(&out, c->dOut[0], sizeof(out), cudaMemcpyDeviceToHost, c->st[0]));
+        CK(cudaStreamSynchronize(c->st[0]));
+        return 0;
+    };
+    if (body()) die("sad");
+    return (int)out;
+}
+
+static int search_host(search_launch_t launch, const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                       size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
 {
     if (!cur || !refPadded || w <= 0 || h <= 0 || (w & 7) || (h & 7) || range < 0 || strd < w + 2 * range || blk1 < blk0 ||
         blk1 > (size_t)(w / 8) * (h / 8))
@@ -325,7 +373,7 @@ extern "C" int xSatd8x8Search(const uint8_t* cur, const uint8_t* refPadded, intp
         int32_t* dBest = nullptr;
         if (cost) { if (ensure(&c->dOut[s], &c->capOut[s], per * costUnit)) return -1; dCost = (uint32_t*)c->dOut[s]; }
         if (best) { if (ensure(&c->dIn[s], &c->capIn[s], per * 12)) return -1; dBest = (int32_t*)c->dIn[s]; }
-        CK(launch_satd8x8_search(dCur, dRef, strd, w, h, range, b0, b0 + nb, dCost, dBest, c->st[s]));
+        CK(launch(dCur, dRef, strd, w, h, range, b0, b0 + nb, dCost, dBest, c->st[s]));
         if (cost) CK(cudaMemcpyAsync(cost + (b0 - blk0) * side * side, dCost, nb * costUnit, cudaMemcpyDeviceToHost, c->st[s]));
         if (best) CK(cudaMemcpyAsync(best + (b0 - blk0) * 3, dBest, nb * 12, cudaMemcpyDeviceToHost, c->st[s]));
     }

@@ -29,6 +29,9 @@ cudaError_t launch_conv_output420(const uint8_t* tiles, uint8_t* Y, intptr_t str
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st);
 cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                   size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
+cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, unsigned* out, cudaStream_t st);
+cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                 size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
 cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st);
 
 } // namespace x266
