@@ -96,6 +96,12 @@ int xDct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int shift
 int xDctNBatch(int log2N, const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd);
 int xDctNBatchDev(int log2N, const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int shift1st, int shift2nd, void* stream);
 
+/* Inverse 32x32 transform ("next" row N3; not in the reference C -- parity unpinned): vertical pass first,
+ * tmp = clip16((G^T * coef + rnd) >> shift1st), out = clip16((tmp * G + rnd) >> shift2nd), clip16 = saturation,
+ * i.e. the HEVC/VVC decoder order and the HM partialButterflyInverse32 arithmetic (shifts 7 / 12 for 8-bit). */
+int xIdct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd);
+int xIdct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int shift1st, int shift2nd, void* stream);
+
 /* one 1-D pass, device pointers (Tier-2 partialButterfly32 on resident data) */
 int xPartialButterfly32Dev(const int16_t* dSrc, int16_t* dDst, int shift, int line, void* stream);
 
@@ -128,6 +134,13 @@ int xSad8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t st
  * angular); pred[i] = 32x32 u8 row-major. */
 int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n);
 int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8_t* dPred, size_t n, void* stream);
+
+/* Fused intra mode decision ("next" row N1; the RTL's Decide channel, src/mkIntra32-wip.bsv:39-48): for each of n
+ * 32x32 blocks (cur[i] = 32x32 u8 row-major, refs[i] as for xIntra32Pred) and each mode m in 0..34,
+ *   cost[i][m] = sum over the 16 8x8 sub-blocks of satd8x8(cur - pred_m)       (src_tb/satd.c:31-118)
+ *   bestMode[i] = argmin_m cost[i][m] (ties -> lowest mode).  Prediction and residual never leave the SM. */
+int xIntra32Decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n);
+int xIntra32DecideDev(const uint8_t* dCur, const uint8_t* dRefs, uint32_t* dCost, int32_t* dBestMode, size_t n, void* stream);
 
 /* ================================================================================================
  * "Next" rows: the encoder's tiled frame stores on the device.

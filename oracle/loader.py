@@ -44,6 +44,7 @@ class Oracle:
         L.orc_partialButterfly.argtypes = [_i16p, _i16p, C.c_int, C.c_int, C.c_int]
         L.orc_partialDense.argtypes = [_i16p, _i16p, C.c_int, C.c_int, C.c_int]
         L.orc_dct2d.argtypes = [_i16p, _i16p, C.c_int, C.c_int, C.c_int]
+        L.orc_idct2d.argtypes = [_i16p, _i16p, C.c_int, C.c_int, C.c_int]
         L.orc_satd8x8.argtypes = [_i16p]
         L.orc_satd8x8.restype = C.c_int
         L.orc_satd_search_block.argtypes = [_u8p, C.c_int, _u8p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, _u32p]
@@ -54,6 +55,7 @@ class Oracle:
         L.orc_sad.argtypes = [_u8p, C.c_ssize_t, _u8p, C.c_ssize_t, C.c_int, C.c_int]
         L.orc_sad.restype = C.c_uint32
         L.orc_intra32.argtypes = [_u8p, _u8p, C.c_int, _u8p]
+        L.orc_intra32_decide.argtypes = [_u8p, _u8p, _u8p, _u32p, C.c_void_p]
         L.orc_intra_mode_angle.argtypes = [C.c_int]
         L.orc_intra_mode_angle.restype = C.c_int
         L.orc_conv_input_fmt.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_ssize_t, C.c_int, C.c_int]
@@ -87,6 +89,15 @@ class Oracle:
         rc = self.lib.orc_dct_batch(src.ravel(), dst.ravel(), n, log2n, shift1, shift2, threads)
         assert rc == 0
         return dst
+
+    def idct(self, src, log2n=5, shift1=7, shift2=12):
+        src = np.ascontiguousarray(src, np.int16)
+        bs = 1 << (2 * log2n)
+        flat = src.reshape(-1, bs)
+        dst = np.empty_like(flat)
+        for i in range(flat.shape[0]):
+            self.lib.orc_idct2d(flat[i], dst[i], log2n, shift1, shift2)
+        return dst.reshape(src.shape)
 
     # --- SATD ------------------------------------------------------------------------------
     def satd(self, diff, threads=1):
@@ -127,6 +138,13 @@ class Oracle:
         pred = np.empty((32, 32), np.uint8)
         self.lib.orc_intra32(np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(top, np.uint8), mode, pred)
         return pred
+
+    def intra32_decide(self, cur, left, top):
+        cost = np.zeros(35, np.uint32)
+        best = C.c_int32(0)
+        self.lib.orc_intra32_decide(np.ascontiguousarray(cur, np.uint8).ravel(), np.ascontiguousarray(left, np.uint8),
+                                    np.ascontiguousarray(top, np.uint8), cost, C.byref(best))
+        return cost, best.value
 
     # --- tiled frames ----------------------------------------------------------------------
     def conv_input_fmt(self, Y, U, V):

@@ -120,6 +120,33 @@ void orc_dct2d(const int16_t* src, int16_t* dst, int log2n, int shift1, int shif
     orc_partialButterfly(coef, dst, shift2, n, log2n);
 }
 
+/* "Next" row N3: inverse transform (PARITY UNPINNED: no inverse exists in the reference).  Defined as the HEVC/VVC
+ * decoder and the HM model partialButterflyInverse32 do it: for every column j of the stored block,
+ *   dst[j*N + k] = clip16((sum_u G_N[u][k] * src[u*line + j] + (1 << (shift-1))) >> shift)
+ * (transposed store, saturating), applied twice. */
+static int16_t orc_clip16(int v) { return (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
+
+void orc_partialInverse(const int16_t* src, int16_t* dst, int shift, int line, int log2n)
+{
+    const int n = 1 << log2n, add = 1 << (shift - 1);
+    int j, k, u;
+    for (j = 0; j < line; j++)
+        for (k = 0; k < n; k++)
+        {
+            int acc = 0;
+            for (u = 0; u < n; u++) acc += orc_g(u * (32 / n), k) * src[u * line + j];
+            dst[j * n + k] = orc_clip16((acc + add) >> shift);
+        }
+}
+
+void orc_idct2d(const int16_t* src, int16_t* dst, int log2n, int shift1, int shift2)
+{
+    int16_t tmp[32 * 32];
+    const int n = 1 << log2n;
+    orc_partialInverse(src, tmp, shift1, n, log2n);
+    orc_partialInverse(tmp, dst, shift2, n, log2n);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * A4. 8x8 Hadamard SATD.  src_tb/satd.c:31-118 (satd8x8).
  * Rows then columns, each a 3-stage Hadamard with partner distances 4, 2, 1 (satd.c:41-66 and
@@ -333,6 +360,32 @@ void orc_intra32(const uint8_t left[64], const uint8_t top[65], int mode, uint8_
             }
         }
     }
+}
+
+/* Fused intra mode decision ("next" row N1): cost[m] = sum over the 16 8x8 sub-blocks of satd8x8(cur - pred_m). */
+void orc_intra32_decide(const uint8_t cur[1024], const uint8_t left[64], const uint8_t top[65], uint32_t cost[35], int32_t* bestMode)
+{
+    int m, sb, x, y, bm = 0;
+    for (m = 0; m < 35; m++)
+    {
+        uint8_t pred[1024];
+        uint32_t c = 0;
+        orc_intra32(left, top, m, pred);
+        for (sb = 0; sb < 16; sb++)
+        {
+            int16_t d[64];
+            for (y = 0; y < 8; y++)
+                for (x = 0; x < 8; x++)
+                {
+                    const int o = ((sb >> 2) * 8 + y) * 32 + (sb & 3) * 8 + x;
+                    d[y * 8 + x] = (int16_t)((int)cur[o] - (int)pred[o]);
+                }
+            c += (uint32_t)orc_satd8x8(d);
+        }
+        cost[m] = c;
+        if (c < cost[bm]) bm = m;
+    }
+    *bestMode = bm;
 }
 
 /* ------------------------------------------------------------------------------------------------

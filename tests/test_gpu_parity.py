@@ -361,3 +361,41 @@ def test_sad_search(x266, orc, rng_px):
     assert np.array_equal(cost, wc) and np.array_equal(best, wb)
     c, b = x266.xSad8x8Search(cur, refp, rng_px, 7, 20)
     assert np.array_equal(c, wc[7:20]) and np.array_equal(b, wb[7:20])
+
+
+# ------------------------------------------------------------------ fused intra mode decision ("next" N1)
+def test_intra32_decide(x266, orc):
+    r = np.random.default_rng(12)
+    n = 40
+    refs = r.integers(0, 256, (n, 129)).astype(np.uint8)
+    cur = r.integers(0, 256, (n, 32, 32)).astype(np.uint8)
+    # plant exact predictions so that specific modes must win with cost 0
+    for i, m in enumerate((0, 1, 2, 10, 18, 26, 34, 7, 13, 21, 29)):
+        cur[i] = orc.intra32(refs[i, :64], refs[i, 64:], m)
+    refs[n - 1] = 255; cur[n - 1] = 0          # extreme flat residual -255
+    cost, best = x266.xIntra32Decide(cur, refs)
+    for i in range(n):
+        wc, wb = orc.intra32_decide(cur[i], refs[i, :64], refs[i, 64:])
+        assert np.array_equal(cost[i], wc), i
+        assert best[i] == wb
+    for i, m in enumerate((0, 1, 2, 10, 18, 26, 34, 7, 13, 21, 29)):
+        assert cost[i, m] == 0 and cost[i, best[i]] == 0
+
+
+# ------------------------------------------------------------------------ inverse transform ("next" N3)
+def test_idct32_vs_oracle_and_roundtrip(x266, orc, vectors):
+    r = np.random.default_rng(4)
+    blocks = [orc.residual(64 * 1024, 8, 2).reshape(-1, 32, 32), r.integers(-2000, 2000, (64, 32, 32)).astype(np.int16),
+              np.stack([np.full((32, 32), v, np.int16) for v in (0, 1, -1, 32767, -32768)]), vectors["dct_out_4_11"]]
+    for x in blocks:
+        for sh in ((7, 12), (7, 10), (1, 1), (16, 16)):
+            assert np.array_equal(x266.xIdct32Batch(x, *sh), orc.idct(x, 5, *sh)), sh
+    # round trip at the 8-bit operating point (forward 4/11, inverse 7/12): |x - IDCT(DCT(x))| <= 4 on a full 1080p frame
+    # of white-noise residuals (the integer transform pair is not lossless; 3 is the worst case seen on the oracle)
+    x = orc.residual(2040 * 1024, 266, 0)
+    back = x266.xIdct32Batch(x266.xDct32Batch(x, 4, 11), 7, 12)
+    assert int(np.abs(back.astype(np.int32) - x).max()) <= 4
+    # and at the 10-bit operating point of the bench workload (forward 6/11, inverse 7/10)
+    x = orc.residual(2040 * 1024, 266, 1)
+    back = x266.xIdct32Batch(x266.xDct32Batch(x, 6, 11), 7, 10)
+    assert int(np.abs(back.astype(np.int32) - x).max()) <= 16

@@ -48,6 +48,8 @@ def lib():
     L.xGpuTune.argtypes = [i, i]
     L.xDct32Batch.argtypes = [vp, vp, sz, i, i]
     L.xDct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
+    L.xIdct32Batch.argtypes = [vp, vp, sz, i, i]
+    L.xIdct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
     L.xDctNBatch.argtypes = [i, vp, vp, sz, i, i]
     L.xDctNBatchDev.argtypes = [i, vp, vp, sz, i, i, vp]
     L.xPartialButterfly32Dev.argtypes = [vp, vp, i, i, vp]
@@ -61,6 +63,8 @@ def lib():
     L.xConvOutput420Dev.argtypes = [vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, i, i, vp]
     L.xFrameResiDct32.argtypes = [vp, vp, i, i, vp, i, i]
     L.xFrameResiDct32Dev.argtypes = [vp, vp, i, i, vp, i, i, vp]
+    L.xIntra32Decide.argtypes = [vp, vp, vp, vp, sz]
+    L.xIntra32DecideDev.argtypes = [vp, vp, vp, vp, sz, vp]
     L.sad.argtypes = [vp, vp, sz]
     L.sad.restype = i
     L.xSad8x8Search.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp]
@@ -129,6 +133,18 @@ def xDct32Batch(src, shift1st=4, shift2nd=11, out=None):
     return dst
 
 
+def xIdct32Batch(src, shift1st=7, shift2nd=12):
+    src = _np(src, np.int16)
+    assert src.size % 1024 == 0
+    dst = np.empty_like(src)
+    _ck(lib().xIdct32Batch(src.ctypes.data, dst.ctypes.data, src.size // 1024, shift1st, shift2nd), "xIdct32Batch")
+    return dst
+
+
+def xIdct32BatchDev(d_src, d_dst, n_blocks, shift1st, shift2nd, stream=0):
+    _ck(lib().xIdct32BatchDev(d_src, d_dst, n_blocks, shift1st, shift2nd, stream), "xIdct32BatchDev")
+
+
 def xDctNBatch(log2n, src, shift1st, shift2nd):
     src = _np(src, np.int16)
     bs = 1 << (2 * log2n)
@@ -161,6 +177,20 @@ def xSatd8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want
                              cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None),
         "xSatd8x8Search")
     return cost, best
+
+
+def xIntra32Decide(cur, refs):
+    cur = _np(cur, np.uint8).reshape(-1, 1024)
+    refs = _np(refs, np.uint8).reshape(-1, 129)
+    assert cur.shape[0] == refs.shape[0]
+    cost = np.empty((cur.shape[0], 35), np.uint32)
+    best = np.empty(cur.shape[0], np.int32)
+    _ck(lib().xIntra32Decide(cur.ctypes.data, refs.ctypes.data, cost.ctypes.data, best.ctypes.data, cur.shape[0]), "xIntra32Decide")
+    return cost, best
+
+
+def xIntra32DecideDev(d_cur, d_refs, d_cost, d_best, n, stream=0):
+    _ck(lib().xIntra32DecideDev(d_cur, d_refs, d_cost, d_best, n, stream), "xIntra32DecideDev")
 
 
 def sad(a, b):

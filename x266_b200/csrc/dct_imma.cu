@@ -548,6 +548,139 @@ cudaError_t launch_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// "Next" row N3: inverse 32x32 transform with the same matrix, closing the reconstruction loop.
+// Not in the reference C (PARITY UNPINNED); defined as the HEVC/VVC decoder does it and as the HM model
+// partialButterflyInverse32 computes it: vertical pass first,
+//     tmp[y][v] = clip16((sum_u g[u][y] * coef[u][v] + (1 << (s1-1))) >> s1)          (s1 = 7)
+//     out[y][x] = clip16((sum_v tmp[y][v] * g[v][x] + (1 << (s2-1))) >> s2)          (s2 = 12 for 8-bit video)
+// clip16 = saturation to int16 (the standard's Clip3), unlike the forward path's truncating store.
+// Pass 1 contracts over the ROW index of the stored block, so the B fragments (4 consecutive K per byte
+// register) need a 4x4 byte transpose: each lane loads 8-byte pieces of 8 rows and transposes them with 8 PRMT
+// per 16 samples (that also performs the byte-plane split).  The pass-1 accumulators of an m16 tile are exactly
+// one A fragment of pass 2 (rows y stay rows), so again nothing is transposed through memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int IDCT_WARPS = 8;
+
+__device__ __forceinline__ int clip16(int v) { return max(-32768, min(32767, v)); }
+
+__global__ void __launch_bounds__(IDCT_WARPS * 32, 2)
+idct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    // pass 1: A1[mu = y][kappa = u] = g[u][y]
+    uint32_t A1[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; m++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int y = 16 * m + g + 8 * (r & 1);
+            const int kb = 16 * (r >> 1) + 4 * q;
+            A1[m][r] = pack4(c_g8.v[kb + 0][y], c_g8.v[kb + 1][y], c_g8.v[kb + 2][y], c_g8.v[kb + 3][y]);
+        }
+    // pass 2: B2[kappa2][nu] = g[v(kappa2)][x(nu)],  v = 8q + 4(i&1) + 2*hi + (i>>1),  x = sigma(8*tx + g)
+    uint32_t B2[4][2];
+#pragma unroll
+    for (int tx = 0; tx < 4; tx++)
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int x = perm_sigma(8 * tx + g);
+            int v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = c_g8.v[8 * q + 4 * (i & 1) + 2 * rr + (i >> 1)][x];
+            B2[tx][rr] = pack4(v[0], v[1], v[2], v[3]);
+        }
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    const int cAdd1[4] = { add1, add1, add1, add1 };
+    const int cAdd2[4] = { add2, add2, add2, add2 };
+    const int cZero[4] = { 0, 0, 0, 0 };
+
+    const size_t first = (size_t)blockIdx.x * IDCT_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * IDCT_WARPS;
+
+    // lane loads columns 4g..4g+3 (8 bytes) of rows 4q+i and 16+4q+i
+    auto load_block = [&](size_t b, uint2 (&w)[2][4]) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[hh][i] = ld_global_stream_v2(src + b * 1024 + (16 * hh + 4 * q + i) * 32 + g * 4);
+    };
+    uint2 nxt[2][4] = {};
+    if (first < nBlocks) load_block(first, nxt);
+
+    for (size_t b = first; b < nBlocks; b += stride) {
+        // 4x4 byte transposes -> B1 fragments (n-tile t <-> column v = 4g+t)
+        uint32_t BL[4][2], BH[4][2];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t r0 = half ? nxt[hh][0].y : nxt[hh][0].x, r1 = half ? nxt[hh][1].y : nxt[hh][1].x;
+                const uint32_t r2 = half ? nxt[hh][2].y : nxt[hh][2].x, r3 = half ? nxt[hh][3].y : nxt[hh][3].x;
+                const uint32_t t0 = prmt(r0, r1, 0x5140), t1 = prmt(r2, r3, 0x5140);
+                const uint32_t t2 = prmt(r0, r1, 0x7362), t3 = prmt(r2, r3, 0x7362);
+                BL[2 * half][hh] = prmt(t0, t1, 0x5410);     BH[2 * half][hh] = prmt(t0, t1, 0x7632);
+                BL[2 * half + 1][hh] = prmt(t2, t3, 0x5410); BH[2 * half + 1][hh] = prmt(t2, t3, 0x7632);
+            }
+        }
+        if (b + stride < nBlocks) load_block(b + stride, nxt);
+
+        int16_t* d = dst + b * 1024;
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            int r[4][4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int dl[4], dh[4];
+                mma_s8u8(dl, A1[m], BL[t][0], BL[t][1], cAdd1);
+                mma_s8s8(dh, A1[m], BH[t][0], BH[t][1], cZero);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r[t][c] = clip16((dl[c] + dh[c] * 256) >> shift1);
+            }
+            // accumulators of this m16 tile -> pass-2 A fragment (rows y = 16m+g / +8; K slice of this lane)
+            uint32_t AL[4], AH[4];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int hi = 0; hi < 2; hi++) {
+                    const uint32_t p0 = prmt(r[2 * hi][2 * h], r[2 * hi][2 * h + 1], 0x5140);
+                    const uint32_t p1 = prmt(r[2 * hi + 1][2 * h], r[2 * hi + 1][2 * h + 1], 0x5140);
+                    AL[h + 2 * hi] = prmt(p0, p1, 0x5410);
+                    AH[h + 2 * hi] = prmt(p0, p1, 0x7632);
+                }
+            int r2[4][4];
+#pragma unroll
+            for (int tx = 0; tx < 4; tx++) {
+                int dl[4], dh[4];
+                mma_u8s8(dl, AL, B2[tx][0], B2[tx][1], cAdd2);
+                mma_s8s8(dh, AH, B2[tx][0], B2[tx][1], cZero);
+#pragma unroll
+                for (int c = 0; c < 4; c++) r2[tx][c] = clip16((dl[c] + dh[c] * 256) >> shift2);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint4 o;
+                o.x = prmt(r2[0][2 * h], r2[0][2 * h + 1], 0x5410);
+                o.y = prmt(r2[1][2 * h], r2[1][2 * h + 1], 0x5410);
+                o.z = prmt(r2[2][2 * h], r2[2][2 * h + 1], 0x5410);
+                o.w = prmt(r2[3][2 * h], r2[3][2 * h + 1], 0x5410);
+                st_global_stream(d + (16 * m + 8 * h + g) * 32 + q * 8, o);
+            }
+        }
+    }
+}
+
+cudaError_t launch_idct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
+{
+    if (nBlocks == 0) return cudaSuccess;
+    const size_t want = (nBlocks + IDCT_WARPS - 1) / IDCT_WARPS;
+    const size_t cap = (size_t)sm_count() * 2;
+    idct32_imma_kernel<<<(int)(want < cap ? want : cap), IDCT_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---- configuration table (index = tuning id).  Shipped default = 6 (8 warps, 2 CTAs/SM, register
 // double-buffered 128-bit global loads): 95.7 % of the measured HBM roofline on B200 vs 86.7 % for the
 // best TMA-ring instantiation (profiles/r01_tune_dct.log).

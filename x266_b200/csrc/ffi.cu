@@ -235,6 +235,26 @@ extern "C" int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int
                        });
 }
 
+extern "C" int xIdct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int s1, int s2, void* stream)
+{
+    if (!shifts_ok(s1, s2) || (nBlocks && (!dSrc || !dDst))) return fail("xIdct32BatchDev", cudaSuccess);
+    if ((reinterpret_cast<uintptr_t>(dSrc) | reinterpret_cast<uintptr_t>(dDst)) & 15) return fail("xIdct32BatchDev: 16-byte alignment", cudaSuccess);
+    CK(launch_idct32_imma(dSrc, dDst, nBlocks, s1, s2, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xIdct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2)
+{
+    if (!shifts_ok(s1, s2) || (nBlocks && (!src || !dst))) return fail("xIdct32Batch", cudaSuccess);
+    if (nBlocks == 0) return 0;
+    Ctx* c;
+    if (ctx_get(&c)) return -1;
+    return run_chunked(*c, src, 2048, dst, 2048, nBlocks, 8192,
+                       [&](void* di, void* dO, size_t n, cudaStream_t st) {
+                           return launch_idct32_imma((const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
+                       });
+}
+
 extern "C" int xDctNBatchDev(int log2N, const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int s1, int s2, void* stream)
 {
     if (log2N == 5) return xDct32BatchDev(dSrc, dDst, nBlocks, s1, s2, stream);
@@ -412,6 +432,43 @@ extern "C" int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* p
         CK(cudaMemcpyAsync(dMode, mode + p0, np, cudaMemcpyHostToDevice, c->st[s]));
         CK(launch_intra32(dRefs, dMode, (uint8_t*)c->dOut[s], np, c->st[s]));
         CK(cudaMemcpyAsync(pred + p0 * 1024, c->dOut[s], np * 1024, cudaMemcpyDeviceToHost, c->st[s]));
+    }
+    for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(c->st[s]));
+    return 0;
+}
+
+extern "C" int xIntra32DecideDev(const uint8_t* dCur, const uint8_t* dRefs, uint32_t* dCost, int32_t* dBestMode, size_t n, void* stream)
+{
+    if (n && (!dCur || !dRefs || !dCost || !dBestMode)) return fail("xIntra32DecideDev", cudaSuccess);
+    if (reinterpret_cast<uintptr_t>(dCur) & 3) return fail("xIntra32DecideDev: 4-byte alignment", cudaSuccess);
+    CK(launch_intra32_decide(dCur, dRefs, dCost, dBestMode, n, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xIntra32Decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n)
+{
+    if (n && (!cur || !refs || !cost || !bestMode)) return fail("xIntra32Decide", cudaSuccess);
+    if (n == 0) return 0;
+    Ctx* c;
+    if (ctx_get(&c)) return -1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t per = (size_t)1 << 14;
+    size_t i = 0;
+    for (size_t p0 = 0; p0 < n; p0 += per, i++) {
+        const int s = (int)(i % SLOTS);
+        const size_t np = (n - p0) < per ? (n - p0) : per;
+        const size_t refOff = per * 1024, costOff = 0, bestOff = (per * 35 * 4 + 255) & ~(size_t)255;
+        if (ensure(&c->dIn[s], &c->capIn[s], per * 1024 + per * 129 + 256)) return -1;
+        if (ensure(&c->dOut[s], &c->capOut[s], bestOff + per * 4)) return -1;
+        uint8_t* dCur = (uint8_t*)c->dIn[s];
+        uint8_t* dRefs = dCur + refOff;
+        uint32_t* dCost = (uint32_t*)((uint8_t*)c->dOut[s] + costOff);
+        int32_t* dBest = (int32_t*)((uint8_t*)c->dOut[s] + bestOff);
+        CK(cudaMemcpyAsync(dCur, cur + p0 * 1024, np * 1024, cudaMemcpyHostToDevice, c->st[s]));
+        CK(cudaMemcpyAsync(dRefs, refs + p0 * 129, np * 129, cudaMemcpyHostToDevice, c->st[s]));
+        CK(launch_intra32_decide(dCur, dRefs, dCost, dBest, np, c->st[s]));
+        CK(cudaMemcpyAsync(cost + p0 * 35, dCost, np * 35 * 4, cudaMemcpyDeviceToHost, c->st[s]));
+        CK(cudaMemcpyAsync(bestMode + p0, dBest, np * 4, cudaMemcpyDeviceToHost, c->st[s]));
     }
     for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(c->st[s]));
     return 0;

@@ -12,6 +12,7 @@ void count_launch();            // bumps the library-wide kernel launch counter
 cudaError_t launch_dct32_bfly(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 cudaError_t launch_dct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 cudaError_t launch_dct16_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
+cudaError_t launch_idct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 void set_small_dct_cuda_cores(int on);   // tuning/diagnostic: CUDA-core dctN kernels for N=8,16 instead of IMMA
 void set_imma_config(int id);   // tuning/diagnostic: selects a (warps, stages, CTAs/SM, staging) instantiation
@@ -29,6 +30,7 @@ cudaError_t launch_conv_output420(const uint8_t* tiles, uint8_t* Y, intptr_t str
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st);
 cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                   size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
+cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st);
 cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, unsigned* out, cudaStream_t st);
 cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                  size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
