@@ -249,50 +249,68 @@ def main():
     e2e_value = world * e2e_blocks * e2e_steps / e2e_s
     e2e_ok = bool(np.array_equal(hout_np, dst[:e2e_blocks].cpu().numpy()))
 
-    # ---- SATD secondary numbers (same run, rank-local, reported per GPU)
+    # ---- secondary numbers: the other kernels of the path, same run.  Every rank runs the same per-GPU workload
+    #      (independent units, no collective), times are max over ranks, values are whole-job aggregates.
     secondary = []
     if not args.no_secondary:
         peak, peak_src = measured_peaks()
-        n_c = 1 << 24                                                     # 16.8M candidates = 2.1 GB of diffs
+
+        def timed(fn, reps, warm=2):
+            for _ in range(warm):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return max_over_ranks(e0.elapsed_time(e1) / reps)
+
+        def hbm(metric, units, bytes_per_unit, ms, note=None):
+            gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9            # per GPU
+            e = {"metric": metric, "value": world * units / (ms * 1e-3), "n_gpus": world, "ms_per_launch": ms,
+                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                              "algorithmic_bytes_per_unit": bytes_per_unit}}
+            if note:
+                e["config"] = note
+            secondary.append(e)
+
+        n_c = 1 << 24                                                     # 16.8M candidates = 2.1 GB of diffs per GPU
         d = torch.randint(-255, 256, (n_c, 64), device=dev, generator=g, dtype=torch.int16)
         o = torch.empty(n_c, device=dev, dtype=torch.int32)
-        for _ in range(3):
-            xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), n_c, st)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(10):
-            xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), n_c, st)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        gbs = n_c * 132 / (ms * 1e-3) / 1e9
-        secondary.append({"metric": "satd8x8_batch_candidates_per_s_per_gpu", "value": n_c / (ms * 1e-3), "ms_per_launch": ms,
-                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                       "traffic": None, "algorithmic_bytes_per_candidate": 132}})
+        ms = timed(lambda: xb.xSatd8x8BatchDev(d.data_ptr(), o.data_ptr(), n_c, st), 10)
+        hbm("satd8x8_batch_candidates_per_s", n_c, 132, ms, "16.8M precomputed 9-bit 8x8 differences per GPU")
         del d, o
-        # config 3: full search +-32 over one 1920x1080 frame, argmin + full u32 cost surface
+        # config 3: full search +-32 over one 1920x1080 frame per GPU, argmin + full u32 cost surface
         w, h, rg = 1920, 1080, 32
         cur = torch.randint(0, 256, (h, w), device=dev, generator=g, dtype=torch.uint8)
         refp = torch.randint(0, 256, (h + 2 * rg, w + 2 * rg), device=dev, generator=g, dtype=torch.uint8)
         nb = (w // 8) * (h // 8)
         cost = torch.empty((nb, 65, 65), device=dev, dtype=torch.int32)
         best = torch.empty((nb, 3), device=dev, dtype=torch.int32)
-        call = lambda: xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 2 * rg, w, h, rg, 0, nb,   # noqa: E731
-                                            cost.data_ptr(), best.data_ptr(), st)
-        for _ in range(2):
-            call()
-        e0.record(stream)
-        for _ in range(5):
-            call()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        cands = nb * 65 * 65
-        secondary.append({"metric": "satd8x8_search_candidates_per_s_per_gpu", "value": cands / (ms * 1e-3), "ms_per_frame": ms,
-                          "config": "config3: 1920x1080, +-32, u32 cost surface + argmin",
-                          "roofline": {"bound": "int32-alu (not HBM)", "achieved": 551903296 / (ms * 1e-3) / 1e9, "peak": peak,
-                                       "unit": "GB/s", "frac": 551903296 / (ms * 1e-3) / 1e9 / peak, "traffic": None}})
+        for name, fn in (("satd8x8_search_candidates_per_s", xb.xSatd8x8SearchDev), ("sad8x8_search_candidates_per_s", xb.xSad8x8SearchDev)):
+            ms = timed(lambda: fn(cur.data_ptr(), refp.data_ptr(), w + 2 * rg, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st), 5)
+            cands = nb * 65 * 65
+            secondary.append({"metric": name, "value": world * cands / (ms * 1e-3), "n_gpus": world, "ms_per_frame": ms,
+                              "config": "config3: 1920x1080 per GPU, +-32, u32 cost surface + argmin",
+                              "roofline": {"bound": "shared-memory / INT32 issue (not HBM)", "achieved": 551903296 / (ms * 1e-3) / 1e9,
+                                           "peak": peak, "unit": "GB/s", "frac": 551903296 / (ms * 1e-3) / 1e9 / peak, "traffic": None}})
         del cur, refp, cost, best
+        # config 4 flavour: the small transforms and the inverse on 256 Mi samples per GPU
+        ns = 1 << 28
+        for log2n, sh in ((4, (3, 10)), (3, (2, 9)), (2, (1, 8))):
+            ms = timed(lambda: xb.xDctNBatchDev(log2n, sp, dp, ns >> (2 * log2n), sh[0], sh[1], st), 10)
+            hbm(f"dct{1 << log2n}_blocks_per_s", ns >> (2 * log2n), 4 << (2 * log2n), ms)
+        ms = timed(lambda: xb.xIdct32BatchDev(sp, dp, ns >> 10, 7, 10, st), 10)
+        hbm("idct32_blocks_per_s", ns >> 10, 4096, ms, "parity unpinned (no inverse in the reference)")
+        npred = 1 << 19
+        refs = torch.randint(0, 256, (npred, 129), device=dev, generator=g, dtype=torch.uint8)
+        modes = (torch.arange(npred, device=dev) % 35).to(torch.uint8)
+        pred = torch.empty((npred, 1024), device=dev, dtype=torch.uint8)
+        ms = timed(lambda: xb.xIntra32PredDev(refs.data_ptr(), modes.data_ptr(), pred.data_ptr(), npred, st), 10)
+        hbm("intra32_predictions_per_s", npred, 1154, ms, "parity unpinned (no C model in the reference)")
+        del refs, modes, pred
 
     # ---- CPU baseline: the reference C on this box's host cores, bounded sample, rank 0 at N=1 only
     cpu = None

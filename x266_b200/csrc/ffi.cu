@@ -23,6 +23,7 @@ namespace x266 {
 // ------------------------------------------------------------------------------------------------
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_dctVariant{X266_DCT_AUTO};
+static std::atomic<size_t> g_dctChunk{16384};      // blocks per pipeline chunk of the host-pointer DCT path (xGpuTune key 4)
 static thread_local char t_err[512] = "";
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -212,6 +213,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 1) { set_search_v1(value); return 0; }
     if (key == 2) { set_satd_cuda_cores(value); return 0; }
     if (key == 3) { set_small_dct_cuda_cores(value); return 0; }
+    if (key == 4 && value > 0) { g_dctChunk.store((size_t)value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }
 
@@ -229,7 +231,7 @@ extern "C" int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int
     if (nBlocks == 0) return 0;
     Ctx* c;
     if (ctx_get(&c)) return -1;
-    return run_chunked(*c, src, 2048, dst, 2048, nBlocks, 8192,
+    return run_chunked(*c, src, 2048, dst, 2048, nBlocks, g_dctChunk.load(),
                        [&](void* di, void* dO, size_t n, cudaStream_t st) {
                            return dct32_dispatch((const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
                        });
