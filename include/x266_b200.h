@@ -91,6 +91,10 @@ int xGpuTune(int key, int value);
 int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd);
 int xDct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int shift1st, int shift2nd, void* stream);
 
+/* Multi-GPU form: blocks are independent, so GPU g of nGpus transforms the contiguous range
+ * [g*N/G, (g+1)*N/G) of the host arrays; one host thread per device, no collective.  nGpus <= 0 = all visible. */
+int xDct32BatchMultiGpu(const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd, int nGpus);
+
 /* N x N forward transform, log2N in {2,3,4,5}; matrix rows g_t32[k*32/N][0..N) (dct32.c:109-143),
  * shifts per src/mkDct32.bsv:93-98. */
 int xDctNBatch(int log2N, const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd);

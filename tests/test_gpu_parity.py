@@ -399,3 +399,14 @@ def test_idct32_vs_oracle_and_roundtrip(x266, orc, vectors):
     x = orc.residual(2040 * 1024, 266, 1)
     back = x266.xIdct32Batch(x266.xDct32Batch(x, 6, 11), 7, 10)
     assert int(np.abs(back.astype(np.int32) - x).max()) <= 16
+
+
+def test_multi_gpu_host_entry(x266, orc):
+    """xDct32BatchMultiGpu: contiguous shards, one host thread per device (all visible devices; 1 is fine)."""
+    import torch
+    x = orc.residual(20000 * 1024, 77, 1)
+    want = orc.dct(x.reshape(-1, 32, 32), 5, 6, 11, threads=8).ravel()
+    for n in sorted({1, torch.cuda.device_count()}):
+        assert np.array_equal(x266.xDct32BatchMultiGpu(x, 6, 11, n_gpus=n), want)
+    with pytest.raises(x266.X266Error):
+        x266.xDct32BatchMultiGpu(x, 6, 11, n_gpus=torch.cuda.device_count() + 1)

@@ -48,6 +48,7 @@ def lib():
     L.xGpuTune.argtypes = [i, i]
     L.xDct32Batch.argtypes = [vp, vp, sz, i, i]
     L.xDct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
+    L.xDct32BatchMultiGpu.argtypes = [vp, vp, sz, i, i, i]
     L.xIdct32Batch.argtypes = [vp, vp, sz, i, i]
     L.xIdct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
     L.xDctNBatch.argtypes = [i, vp, vp, sz, i, i]
@@ -130,6 +131,14 @@ def xDct32Batch(src, shift1st=4, shift2nd=11, out=None):
     assert src.size % 1024 == 0
     dst = np.empty_like(src) if out is None else out
     _ck(lib().xDct32Batch(src.ctypes.data, dst.ctypes.data, src.size // 1024, shift1st, shift2nd), "xDct32Batch")
+    return dst
+
+
+def xDct32BatchMultiGpu(src, shift1st=4, shift2nd=11, n_gpus=0, out=None):
+    src = _np(src, np.int16)
+    assert src.size % 1024 == 0
+    dst = np.empty_like(src) if out is None else out
+    _ck(lib().xDct32BatchMultiGpu(src.ctypes.data, dst.ctypes.data, src.size // 1024, shift1st, shift2nd, n_gpus), "xDct32BatchMultiGpu")
     return dst
 
 

@@ -14,7 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 namespace x266 {
 
@@ -235,6 +238,34 @@ extern "C" int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int
                        [&](void* di, void* dO, size_t n, cudaStream_t st) {
                            return dct32_dispatch((const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
                        });
+}
+
+extern "C" int xDct32BatchMultiGpu(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, int nGpus)
+{
+    // blocks are independent -> GPU g of G owns the contiguous range [g*N/G, (g+1)*N/G); one host
+    // thread per device drives that device's chunked pipeline; no collective, no peer traffic.
+    int have = 0;
+    CK(cudaGetDeviceCount(&have));
+    if (nGpus <= 0) nGpus = have;
+    if (nGpus > have || !shifts_ok(s1, s2) || (nBlocks && (!src || !dst))) return fail("xDct32BatchMultiGpu", cudaSuccess);
+    if (nBlocks == 0) return 0;
+    int prev = 0;
+    CK(cudaGetDevice(&prev));
+    std::vector<int> rc(nGpus, 0);
+    std::vector<std::string> err(nGpus);
+    std::vector<std::thread> th;
+    for (int g = 0; g < nGpus; g++)
+        th.emplace_back([&, g]() {
+            const size_t lo = nBlocks * (size_t)g / nGpus, hi = nBlocks * (size_t)(g + 1) / nGpus;
+            if (cudaSetDevice(g) != cudaSuccess) { rc[g] = -1; err[g] = "cudaSetDevice failed"; return; }
+            rc[g] = xDct32Batch(src + lo * 1024, dst + lo * 1024, hi - lo, s1, s2);
+            if (rc[g]) err[g] = t_err;
+        });
+    for (auto& t : th) t.join();
+    cudaSetDevice(prev);
+    for (int g = 0; g < nGpus; g++)
+        if (rc[g]) { snprintf(t_err, sizeof(t_err), "xDct32BatchMultiGpu: device %d: %s", g, err[g].c_str()); return -1; }
+    return 0;
 }
 
 extern "C" int xIdct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int s1, int s2, void* stream)
