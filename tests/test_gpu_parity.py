@@ -410,3 +410,44 @@ def test_multi_gpu_host_entry(x266, orc):
         assert np.array_equal(x266.xDct32BatchMultiGpu(x, 6, 11, n_gpus=n), want)
     with pytest.raises(x266.X266Error):
         x266.xDct32BatchMultiGpu(x, 6, 11, n_gpus=torch.cuda.device_count() + 1)
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_full_size_config5_two_implementations_agree(x266, orc):
+    """BASELINE config 5 at the bench size (64 frames of 8K = 2 073 600 blocks, 4.25 GB) is too big for the CPU
+    oracle, so: (1) the tensor-core kernel and the independent CUDA-core butterfly kernel must agree bit for bit
+    on the whole batch, (2) a deterministic sample of blocks (first, last, strided) is checked against the oracle,
+    (3) the run is repeatable bit for bit."""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 64 * 32400
+    g = torch.Generator(device=dev); g.manual_seed(266)
+    src = (torch.randint(0, 1024, (n, 32, 32), device=dev, generator=g, dtype=torch.int16)
+           - torch.randint(0, 1024, (n, 32, 32), device=dev, generator=g, dtype=torch.int16))
+    a, b = torch.empty_like(src), torch.empty_like(src)
+    st = torch.cuda.current_stream().cuda_stream
+    x266.set_dct_variant(x266.DCT_IMMA); x266.xDct32BatchDev(src.data_ptr(), a.data_ptr(), n, 6, 11, st)
+    x266.set_dct_variant(x266.DCT_BFLY); x266.xDct32BatchDev(src.data_ptr(), b.data_ptr(), n, 6, 11, st)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    x266.set_dct_variant(x266.DCT_IMMA); x266.xDct32BatchDev(src.data_ptr(), b.data_ptr(), n, 6, 11, st)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    x266.set_dct_variant(x266.DCT_AUTO)
+    idx = torch.cat([torch.arange(0, 512), torch.arange(n - 512, n), torch.arange(0, n, 4099)]).to(dev)
+    xs, ys = src[idx].cpu().numpy(), a[idx].cpu().numpy()
+    assert np.array_equal(ys, orc.dct(xs, 5, 6, 11, threads=8))
+
+
+@pytest.mark.parametrize("cfg", list(range(16)))
+def test_every_imma_instantiation_is_bit_exact(x266, orc, cfg):
+    """all 16 (warps, stages, CTAs/SM, staging) instantiations of the tensor-core kernel, ragged batch"""
+    x = orc.residual(5003 * 1024, 40 + cfg, 2)
+    want = orc.dct(x.reshape(-1, 32, 32), 5, 4, 11, threads=8).ravel()
+    x266.set_dct_variant(x266.DCT_IMMA)
+    x266.tune(0, cfg)
+    try:
+        assert np.array_equal(x266.xDct32Batch(x, 4, 11), want)
+    finally:
+        x266.tune(0, -1)
+        x266.set_dct_variant(x266.DCT_AUTO)
