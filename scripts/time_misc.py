@@ -36,8 +36,11 @@ nd = 1 << 17
 curb = torch.randint(0, 256, (nd, 1024), device=dev, dtype=torch.uint8)
 costs = torch.empty((nd, 35), device=dev, dtype=torch.int32)
 bestm = torch.empty((nd,), device=dev, dtype=torch.int32)
-ms = timeit(lambda: xb.xIntra32DecideDev(curb.data_ptr(), refs.data_ptr(), costs.data_ptr(), bestm.data_ptr(), nd, st), reps=3)
-print(f"intra32 decide (35 modes x 16 SATD8x8 per block) n={nd}: {ms:7.3f} ms  {nd / ms / 1e3:7.2f} M blocks/s  {nd * 35 * 16 / ms / 1e6:7.2f} G (mode,8x8) SATDs/s", flush=True)
+for v1 in (1, 0):
+    xb.tune(5, v1)
+    ms = timeit(lambda: xb.xIntra32DecideDev(curb.data_ptr(), refs.data_ptr(), costs.data_ptr(), bestm.data_ptr(), nd, st), reps=3)
+    print(f"intra32 decide {('tensor-core','cuda-core')[v1]} (35 modes x 16 SATD8x8 per block) n={nd}: {ms:7.3f} ms  {nd / ms / 1e3:7.2f} M blocks/s  {nd * 35 * 16 / ms / 1e6:7.2f} G (mode,8x8) SATDs/s", flush=True)
+xb.tune(5, 0)
 # fused residual + DCT32 from tiled frames: one launch over 8 stacked 8K luma frames (7680 x 34816)
 w, h = 7680, 4352 * 8
 ntile = (w // 16) * (h // 16)

@@ -364,7 +364,10 @@ def test_sad_search(x266, orc, rng_px):
 
 
 # ------------------------------------------------------------------ fused intra mode decision ("next" N1)
-def test_intra32_decide(x266, orc):
+@pytest.mark.parametrize("v1", [0, 1])
+def test_intra32_decide(x266, orc, v1):
+    """v1 = 0: tensor-core kernel (horizontal modes on the transposed problem); v1 = 1: CUDA-core kernel"""
+    x266.tune(5, v1)
     r = np.random.default_rng(12)
     n = 40
     refs = r.integers(0, 256, (n, 129)).astype(np.uint8)
@@ -374,6 +377,7 @@ def test_intra32_decide(x266, orc):
         cur[i] = orc.intra32(refs[i, :64], refs[i, 64:], m)
     refs[n - 1] = 255; cur[n - 1] = 0          # extreme flat residual -255
     cost, best = x266.xIntra32Decide(cur, refs)
+    x266.tune(5, 0)
     for i in range(n):
         wc, wb = orc.intra32_decide(cur[i], refs[i, :64], refs[i, 64:])
         assert np.array_equal(cost[i], wc), i

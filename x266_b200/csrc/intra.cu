@@ -229,11 +229,194 @@ intra32_decide_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mode decision v2 (shipped): the 16 sub-blocks of one (block, mode) are exactly one m16 tile of the
+// tensor-core SATD (satd.cu): A = the 8-bit prediction pixels (a single u8 plane, no byte split), B = the +-1
+// Sylvester matrix, 16 IMMA per mode.  By linearity the cost is sum |T(cur) - T(pred)| against the transform of
+// the current block, computed once per block with the same MMA and parked in shared memory in accumulator
+// layout.  Horizontal modes (2..17) are evaluated on the TRANSPOSED problem: pred_h = P_v^T where P_v is the
+// vertical-family routine run on the left reference, and SATD(X^T) = SATD(X) for every 8x8 block (H is
+// symmetric), so one SWAR row generator (8 pixels of one prediction row = one A-fragment register pair,
+// 2 pixels per 32-bit multiply-add) serves all 33 angular modes.  One warp owns one mode at a time.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t intra_row4(uint32_t a, uint32_t b, int f)
+{
+    // 4 pixels: ((32-f)*a + f*b + 16) >> 5 per byte, two 16-bit lanes per multiply-add
+    const uint32_t ae = a & 0x00FF00FFu, ao = (a >> 8) & 0x00FF00FFu;
+    const uint32_t be = b & 0x00FF00FFu, bo = (b >> 8) & 0x00FF00FFu;
+    const uint32_t pe = ((ae * (uint32_t)(32 - f) + be * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
+    const uint32_t po = ((ao * (uint32_t)(32 - f) + bo * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
+    return pe | (po << 8);
+}
+
+__global__ void __launch_bounds__(IDEC_WARPS * 32, 2)
+intra32_decide_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refs, uint32_t* __restrict__ cost,
+                         int32_t* __restrict__ bestMode, size_t n)
+{
+    __shared__ __align__(16) uint8_t scur[2][1024];                 // [0] = block, [1] = its transpose
+    __shared__ __align__(16) int stc[2][32 * 32];                   // T(cur), T(cur^T) in accumulator layout
+    __shared__ __align__(16) uint8_t sraw[144];
+    __shared__ __align__(16) uint8_t strip[IDEC_WARPS][INTRA_STRIP + 16];
+    __shared__ uint32_t scost[35];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int cZero[4] = { 0, 0, 0, 0 };
+
+    // +-1 matrix fragments, identical to satd8x8_imma_kernel: K position 16r+4q+i <-> sample 32s+8q+4r+i, column 8t+g
+    uint32_t B[2][8][2];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int pix = 32 * s + 8 * q + 4 * r + i, nn = 8 * t + g;
+                    v |= ((__popc(nn & pix) & 1) ? 0xFFu : 0x01u) << (8 * i);
+                }
+                B[s][t][r] = v;
+            }
+
+    // this lane's rows: sub-blocks g and g+8 (same column band sx), sub-block rows q and 4+q
+    const int sx = (g & 3) * 8;
+    const int syA = (g >> 2) * 8, syB = syA + 16;
+    uint8_t* sref = strip[warp] + 32 + 4;            // sref[i] = ref[i]; +4 keeps sref-32 word aligned
+    const uint32_t* strip32 = reinterpret_cast<const uint32_t*>(strip[warp]);
+
+    for (size_t p = blockIdx.x; p < n; p += gridDim.x) {
+        {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(cur + p * 1024)[tid];
+            reinterpret_cast<uint32_t*>(scur[0])[tid] = w;
+            const int row = tid >> 3, c0 = (tid & 7) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; i++) scur[1][(c0 + i) * 32 + row] = (uint8_t)(w >> (8 * i));
+            if (tid < 129) sraw[tid] = refs[p * 129 + tid];
+        }
+        __syncthreads();
+        if (warp < 2) {                               // T(cur) (warp 0) and T(cur^T) (warp 1)
+            uint32_t A[2][4];
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const uint2 ra = *reinterpret_cast<const uint2*>(&scur[warp][(syA + 4 * s + q) * 32 + sx]);
+                const uint2 rb = *reinterpret_cast<const uint2*>(&scur[warp][(syB + 4 * s + q) * 32 + sx]);
+                A[s][0] = ra.x; A[s][2] = ra.y; A[s][1] = rb.x; A[s][3] = rb.y;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                int d[4];
+                mma_u8s8(d, A[0], B[0][t][0], B[0][t][1], cZero);
+                mma_u8s8(d, A[1], B[1][t][0], B[1][t][1], d);
+#pragma unroll
+                for (int c = 0; c < 4; c++) stc[warp][(t * 4 + c) * 32 + lane] = d[c];
+            }
+        }
+        __syncthreads();
+        const uint8_t* left = sraw;
+        const uint8_t* top = sraw + 64;
+
+        for (int mode = warp; mode < 35; mode += IDEC_WARPS) {
+            const bool isVer = mode >= 18;
+            const int ang = c_intraAngle[mode];
+            uint32_t A[2][4];
+            if (mode >= 2) {
+                __syncwarp();
+                for (int i = lane; i <= 71; i += 32) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
+                if (ang < 0) {
+                    int inv = 0;
+#pragma unroll
+                    for (int a = 0; a < 8; a++) if (c_intraAngle[11 + a] == ang) inv = c_intraInv[a];
+                    const int k = lane + 1;
+                    if (-k >= ang) {
+                        const int sidx = (k * inv + 128) >> 8;
+                        sref[-k] = isVer ? left[sidx - 1] : top[sidx];
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < 2; s++)
+#pragma unroll
+                    for (int sel = 0; sel < 2; sel++) {
+                        const int row = (sel ? syB : syA) + 4 * s + q;             // distance from the main reference
+                        const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
+                        const int o = 32 + 4 + sx + idx + 1;                        // byte offset of ref[sx+idx+1] in the strip
+                        const uint32_t w0 = strip32[o >> 2], w1 = strip32[(o >> 2) + 1], w2 = strip32[(o >> 2) + 2];
+                        const int sh = (o & 3) * 8;
+                        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
+                        const uint32_t b0 = __funnelshift_rc(w0, w1, sh + 8), b1 = __funnelshift_rc(w1, w2, sh + 8);
+                        A[s][sel] = intra_row4(a0, b0, f);
+                        A[s][2 + sel] = intra_row4(a1, b1, f);
+                    }
+            } else if (mode == 1) {
+                int sum = left[lane] + top[1 + lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const uint32_t dc = (uint32_t)((sum + 32) >> 6) * 0x01010101u;
+#pragma unroll
+                for (int s = 0; s < 2; s++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) A[s][r] = dc;
+            } else {
+                const int tr = top[33], bl = left[32];
+#pragma unroll
+                for (int s = 0; s < 2; s++)
+#pragma unroll
+                    for (int sel = 0; sel < 2; sel++) {
+                        const int row = (sel ? syB : syA) + 4 * s + q;
+                        uint32_t wlo = 0, whi = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int col = sx + c;
+                            const uint32_t v = (uint32_t)(((31 - col) * left[row] + (col + 1) * tr + (31 - row) * top[1 + col] + (row + 1) * bl + 32) >> 6);
+                            if (c < 4) wlo |= v << (8 * c); else whi |= v << (8 * (c - 4));
+                        }
+                        A[s][sel] = wlo;
+                        A[s][2 + sel] = whi;
+                    }
+            }
+            // T(pred) for the 16 sub-blocks, |T(cur) - T(pred)| against the parked transform (transposed one for 2..17)
+            const int* tc = stc[(mode >= 2 && !isVer) ? 1 : 0];
+            unsigned sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                int d[4];
+                mma_u8s8(d, A[0], B[0][t][0], B[0][t][1], cZero);
+                mma_u8s8(d, A[1], B[1][t][0], B[1][t][1], d);
+                sa0 = __sad(d[0], tc[(t * 4 + 0) * 32 + lane], sa0);
+                sa1 = __sad(d[1], tc[(t * 4 + 1) * 32 + lane], sa1);
+                sb0 = __sad(d[2], tc[(t * 4 + 2) * 32 + lane], sb0);
+                sb1 = __sad(d[3], tc[(t * 4 + 3) * 32 + lane], sb1);
+            }
+            unsigned sadA = sa0 + sa1, sadB = sb0 + sb1;                // sub-blocks g and g+8, partial over this lane's columns
+            sadA += __shfl_xor_sync(0xffffffffu, sadA, 1); sadB += __shfl_xor_sync(0xffffffffu, sadB, 1);
+            sadA += __shfl_xor_sync(0xffffffffu, sadA, 2); sadB += __shfl_xor_sync(0xffffffffu, sadB, 2);
+            unsigned c4 = q == 0 ? ((sadA + 2) >> 2) + ((sadB + 2) >> 2) : 0u;
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) c4 += __shfl_xor_sync(0xffffffffu, c4, o);
+            if (lane == 0) scost[mode] = c4;
+        }
+        __syncthreads();
+        if (tid < 35) cost[p * 35 + tid] = scost[tid];
+        if (tid == 0) {
+            unsigned bc = scost[0];
+            int bm = 0;
+            for (int m = 1; m < 35; m++) if (scost[m] < bc) { bc = scost[m]; bm = m; }
+            bestMode[p] = bm;
+        }
+        __syncthreads();
+    }
+}
+
+static int g_decideV1 = 0;
+void set_decide_v1(int on) { g_decideV1 = on; }
+
 cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     const size_t cap = (size_t)sm_count() * 4;
-    intra32_decide_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
+    if (g_decideV1) intra32_decide_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
+    else intra32_decide_v2_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
     count_launch();
     return cudaGetLastError();
 }

@@ -17,6 +17,7 @@ cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, i
 void set_small_dct_cuda_cores(int on);   // tuning/diagnostic: CUDA-core dctN kernels for N=8,16 instead of IMMA
 void set_imma_config(int id);   // tuning/diagnostic: selects a (warps, stages, CTAs/SM, staging) instantiation
 void set_satd_cuda_cores(int on);   // tuning/diagnostic: CUDA-core SATD batch kernel instead of IMMA
+void set_decide_v1(int on);     // tuning/diagnostic: CUDA-core intra decision kernel instead of the tensor-core one
 void set_search_v1(int on);     // tuning/diagnostic: force the v1 (one CTA per block) search kernel
 cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int line, cudaStream_t st);
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
