@@ -100,6 +100,11 @@ int xDct32BatchMultiGpu(const int16_t* src, int16_t* dst, size_t nBlocks, int sh
 int xDctNBatch(int log2N, const int16_t* src, int16_t* dst, size_t nBlocks, int shift1st, int shift2nd);
 int xDctNBatchDev(int log2N, const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int shift1st, int shift2nd, void* stream);
 
+/* Stand-alone transpose stage (src/mkTranspose.bsv:95-99 mkTranspose32x32 on Bit#(8)):
+ * nTiles contiguous 32x32 byte tiles, dst[t][j][i] = src[t][i][j].  (The DCT kernels need no such step.) */
+int xTranspose32x32Batch(const uint8_t* src, uint8_t* dst, size_t nTiles);
+int xTranspose32x32BatchDev(const uint8_t* dSrc, uint8_t* dDst, size_t nTiles, void* stream);
+
 /* Inverse 32x32 transform ("next" row N3; not in the reference C -- parity unpinned): vertical pass first,
  * tmp = clip16((G^T * coef + rnd) >> shift1st), out = clip16((tmp * G + rnd) >> shift2nd), clip16 = saturation,
  * i.e. the HEVC/VVC decoder order and the HM partialButterflyInverse32 arithmetic (shifts 7 / 12 for 8-bit). */

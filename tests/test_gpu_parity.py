@@ -455,3 +455,13 @@ def test_every_imma_instantiation_is_bit_exact(x266, orc, cfg):
     finally:
         x266.tune(0, -1)
         x266.set_dct_variant(x266.DCT_AUTO)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 5000])
+def test_transpose32x32_stage(x266, n):
+    """row A5 as a stand-alone op (mkTranspose32x32 on bytes): streaming 32x32 corner-turn, involution"""
+    x = np.random.default_rng(n).integers(0, 256, (n, 32, 32)).astype(np.uint8)
+    y = x266.xTranspose32x32Batch(x)
+    assert np.array_equal(y, x.transpose(0, 2, 1))
+    if n:
+        assert np.array_equal(x266.xTranspose32x32Batch(y), x)

@@ -66,6 +66,8 @@ def lib():
     L.xFrameResiDct32Dev.argtypes = [vp, vp, i, i, vp, i, i, vp]
     L.xIntra32Decide.argtypes = [vp, vp, vp, vp, sz]
     L.xIntra32DecideDev.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.xTranspose32x32Batch.argtypes = [vp, vp, sz]
+    L.xTranspose32x32BatchDev.argtypes = [vp, vp, sz, vp]
     L.sad.argtypes = [vp, vp, sz]
     L.sad.restype = i
     L.xSad8x8Search.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp]
@@ -186,6 +188,18 @@ def xSatd8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want
                              cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None),
         "xSatd8x8Search")
     return cost, best
+
+
+def xTranspose32x32Batch(src):
+    src = _np(src, np.uint8)
+    assert src.size % 1024 == 0
+    dst = np.empty_like(src)
+    _ck(lib().xTranspose32x32Batch(src.ctypes.data, dst.ctypes.data, src.size // 1024), "xTranspose32x32Batch")
+    return dst
+
+
+def xTranspose32x32BatchDev(d_src, d_dst, n_tiles, stream=0):
+    _ck(lib().xTranspose32x32BatchDev(d_src, d_dst, n_tiles, stream), "xTranspose32x32BatchDev")
 
 
 def xIntra32Decide(cur, refs):

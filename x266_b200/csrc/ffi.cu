@@ -471,6 +471,24 @@ extern "C" int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* p
     return 0;
 }
 
+extern "C" int xTranspose32x32BatchDev(const uint8_t* dSrc, uint8_t* dDst, size_t nTiles, void* stream)
+{
+    if (nTiles && (!dSrc || !dDst)) return fail("xTranspose32x32BatchDev", cudaSuccess);
+    if ((reinterpret_cast<uintptr_t>(dSrc) | reinterpret_cast<uintptr_t>(dDst)) & 15) return fail("xTranspose32x32BatchDev: 16-byte alignment", cudaSuccess);
+    CK(launch_transpose32(dSrc, dDst, nTiles, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xTranspose32x32Batch(const uint8_t* src, uint8_t* dst, size_t nTiles)
+{
+    if (nTiles && (!src || !dst)) return fail("xTranspose32x32Batch", cudaSuccess);
+    if (nTiles == 0) return 0;
+    Ctx* c;
+    if (ctx_get(&c)) return -1;
+    return run_chunked(*c, src, 1024, dst, 1024, nTiles, 16384,
+                       [&](void* di, void* dO, size_t n, cudaStream_t st) { return launch_transpose32((const uint8_t*)di, (uint8_t*)dO, n, st); });
+}
+
 extern "C" int xIntra32DecideDev(const uint8_t* dCur, const uint8_t* dRefs, uint32_t* dCost, int32_t* dBestMode, size_t n, void* stream)
 {
     if (n && (!dCur || !dRefs || !dCost || !dBestMode)) return fail("xIntra32DecideDev", cudaSuccess);

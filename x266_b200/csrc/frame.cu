@@ -66,6 +66,54 @@ conv_output420_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ Y
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stand-alone transpose stage: src/mkTranspose.bsv:95-99 (mkTranspose32x32 on Bit#(8)) is a
+// streaming 32x32 byte corner-turn.  One warp per 1 KiB tile: coalesced 128-bit loads, a 32x33-word-free
+// byte transpose through a padded shared-memory tile, coalesced 128-bit stores.  (Inside the DCT kernels the
+// transpose does not exist as a separate step: see dct_imma.cu.)
+// ------------------------------------------------------------------------------------------------
+constexpr int TR_WARPS = 8;
+
+__global__ void __launch_bounds__(TR_WARPS * 32)
+transpose32_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t nTiles)
+{
+    __shared__ uint8_t tile[TR_WARPS][32][36];          // 36-byte rows: word aligned, 9-word stride spreads the banks
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (size_t t = (size_t)blockIdx.x * TR_WARPS + warp; t < nTiles; t += (size_t)gridDim.x * TR_WARPS) {
+        const uint4* s = reinterpret_cast<const uint4*>(src + t * 1024);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int gi = i * 32 + lane, row = gi >> 1, half = gi & 1;      // 16-byte piece `half` of row `row`
+            const uint4 v = s[gi];
+            uint32_t* d = reinterpret_cast<uint32_t*>(&tile[warp][row][half * 16]);
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncwarp();
+        uint4* o = reinterpret_cast<uint4*>(dst + t * 1024);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int gi = i * 32 + lane, row = gi >> 1, half = gi & 1;      // output row `row` = input column `row`
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = half * 16 + 4 * k;
+                w[k] = tile[warp][c][row] | (tile[warp][c + 1][row] << 8) | (tile[warp][c + 2][row] << 16) | ((uint32_t)tile[warp][c + 3][row] << 24);
+            }
+            o[gi] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_transpose32(const uint8_t* src, uint8_t* dst, size_t nTiles, cudaStream_t st)
+{
+    if (nTiles == 0) return cudaSuccess;
+    const size_t want = (nTiles + TR_WARPS - 1) / TR_WARPS, cap = (size_t)sm_count() * 8;
+    transpose32_kernel<<<(unsigned)(want < cap ? want : cap), TR_WARPS * 32, 0, st>>>(src, dst, nTiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_conv_input_fmt(uint8_t* tiles, const uint8_t* Y, const uint8_t* U, const uint8_t* V, intptr_t strdY,
                                   int width, int height, cudaStream_t st)
 {
