@@ -562,7 +562,13 @@ cudaError_t launch_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int
 // ------------------------------------------------------------------------------------------------
 constexpr int IDCT_WARPS = 8;
 
-__device__ __forceinline__ int clip16(int v) { return max(-32768, min(32767, v)); }
+// pack two s32 into s16x2 with saturation (the standard's Clip3 to int16) in one I2IP.S16.S32.SAT: lo = sat(a), hi = sat(b)
+__device__ __forceinline__ uint32_t pack_sat16(int a, int b)
+{
+    uint32_t r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(b), "r"(a));
+    return r;
+}
 
 __global__ void __launch_bounds__(IDCT_WARPS * 32, 2)
 idct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
@@ -636,7 +642,7 @@ idct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, s
                 mma_s8u8(dl, A1[m], BL[t][0], BL[t][1], cAdd1);
                 mma_s8s8(dh, A1[m], BH[t][0], BH[t][1], cZero);
 #pragma unroll
-                for (int c = 0; c < 4; c++) r[t][c] = clip16((dl[c] + dh[c] * 256) >> shift1);
+                for (int c = 0; c < 4; c++) r[t][c] = (dl[c] + dh[c] * 256) >> shift1;
             }
             // accumulators of this m16 tile -> pass-2 A fragment (rows y = 16m+g / +8; K slice of this lane)
             uint32_t AL[4], AH[4];
@@ -644,10 +650,10 @@ idct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, s
             for (int h = 0; h < 2; h++)
 #pragma unroll
                 for (int hi = 0; hi < 2; hi++) {
-                    const uint32_t p0 = prmt(r[2 * hi][2 * h], r[2 * hi][2 * h + 1], 0x5140);
-                    const uint32_t p1 = prmt(r[2 * hi + 1][2 * h], r[2 * hi + 1][2 * h + 1], 0x5140);
-                    AL[h + 2 * hi] = prmt(p0, p1, 0x5410);
-                    AH[h + 2 * hi] = prmt(p0, p1, 0x7632);
+                    const uint32_t p0 = pack_sat16(r[2 * hi][2 * h], r[2 * hi][2 * h + 1]);          // clip16 + pack
+                    const uint32_t p1 = pack_sat16(r[2 * hi + 1][2 * h], r[2 * hi + 1][2 * h + 1]);
+                    AL[h + 2 * hi] = prmt(p0, p1, 0x6420);
+                    AH[h + 2 * hi] = prmt(p0, p1, 0x7531);
                 }
             int r2[4][4];
 #pragma unroll
@@ -656,15 +662,15 @@ idct32_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, s
                 mma_u8s8(dl, AL, B2[tx][0], B2[tx][1], cAdd2);
                 mma_s8s8(dh, AH, B2[tx][0], B2[tx][1], cZero);
 #pragma unroll
-                for (int c = 0; c < 4; c++) r2[tx][c] = clip16((dl[c] + dh[c] * 256) >> shift2);
+                for (int c = 0; c < 4; c++) r2[tx][c] = (dl[c] + dh[c] * 256) >> shift2;
             }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 uint4 o;
-                o.x = prmt(r2[0][2 * h], r2[0][2 * h + 1], 0x5410);
-                o.y = prmt(r2[1][2 * h], r2[1][2 * h + 1], 0x5410);
-                o.z = prmt(r2[2][2 * h], r2[2][2 * h + 1], 0x5410);
-                o.w = prmt(r2[3][2 * h], r2[3][2 * h + 1], 0x5410);
+                o.x = pack_sat16(r2[0][2 * h], r2[0][2 * h + 1]);
+                o.y = pack_sat16(r2[1][2 * h], r2[1][2 * h + 1]);
+                o.z = pack_sat16(r2[2][2 * h], r2[2][2 * h + 1]);
+                o.w = pack_sat16(r2[3][2 * h], r2[3][2 * h + 1]);
                 st_global_stream(d + (16 * m + 8 * h + g) * 32 + q * 8, o);
             }
         }
