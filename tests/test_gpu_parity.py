@@ -178,9 +178,9 @@ def test_config4_mixed_partition(x266, orc):
 
 
 # ---------------------------------------------------------------------------------------- SATD
-@pytest.fixture(params=["imma", "cuda-core"])
+@pytest.fixture(params=["imma-v2", "cuda-core", "imma-v1", "imma-v2-3cta"])
 def satd_variant(request, x266):
-    x266.tune(2, 1 if request.param == "cuda-core" else 0)
+    x266.tune(2, ["imma-v2", "cuda-core", "imma-v1", "imma-v2-3cta"].index(request.param))
     yield request.param
     x266.tune(2, 0)
 

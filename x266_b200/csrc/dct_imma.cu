@@ -365,9 +365,6 @@ dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
     const size_t nUnits = (nPairs + 7) / 8;
     const size_t first = (size_t)blockIdx.x * D8_WARPS + warp;
     const size_t stride = (size_t)gridDim.x * D8_WARPS;
-    // byte offset of this lane's 8-byte piece inside a 256-byte block pair: block (q>>1), row g, half (q&1)
-    const int laneOff = (q >> 1) * 64 + g * 8 + (q & 1) * 4;        // in int16 units
-
     auto load_unit = [&](size_t u, uint2 (&w)[8]) {
 #pragma unroll
         for (int pp = 0; pp < 8; pp++) {
@@ -376,7 +373,6 @@ dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
             w[pp] = ld_global_stream_v2(src + blk * 64 + g * 8 + (q & 1) * 4);
         }
     };
-    (void)laneOff;
 
     uint2 nxt[8] = {};
     if (first < nUnits) load_unit(first, nxt);

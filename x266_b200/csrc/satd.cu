@@ -130,7 +130,8 @@ satd8x8_batch_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out
 // ------------------------------------------------------------------------------------------------
 constexpr int SATDI_WARPS = 8;
 
-__global__ void __launch_bounds__(SATDI_WARPS * 32, 2)
+template <int MINB, int PF>      // PF = units in flight ahead of the one being transformed
+__global__ void __launch_bounds__(SATDI_WARPS * 32, MINB)
 satd8x8_imma_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,21 +173,27 @@ satd8x8_imma_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out,
         }
     };
 
-    uint4 nxt[2][2] = {};
-    if (first < nUnits) load_unit(first, nxt);
+    uint4 nxt[PF][2][2] = {};
+#pragma unroll
+    for (int k = 0; k < PF; k++)
+        if (first + (size_t)k * stride < nUnits) load_unit(first + (size_t)k * stride, nxt[k]);
 
     for (size_t u = first; u < nUnits; u += stride) {
         // A fragments per plane and k-step: a0 (row g, K 4q+i), a1 (row g+8, same K), a2 (row g, K 16+4q+i), a3 (row g+8)
         uint32_t AL[2][4], AH[2][4];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const uint4 r0 = nxt[s][0], r1 = nxt[s][1];
+            const uint4 r0 = nxt[0][s][0], r1 = nxt[0][s][1];
             AL[s][0] = prmt(r0.x, r0.y, 0x6420); AH[s][0] = prmt(r0.x, r0.y, 0x7531);
             AL[s][2] = prmt(r0.z, r0.w, 0x6420); AH[s][2] = prmt(r0.z, r0.w, 0x7531);
             AL[s][1] = prmt(r1.x, r1.y, 0x6420); AH[s][1] = prmt(r1.x, r1.y, 0x7531);
             AL[s][3] = prmt(r1.z, r1.w, 0x6420); AH[s][3] = prmt(r1.z, r1.w, 0x7531);
         }
-        if (u + stride < nUnits) load_unit(u + stride, nxt);
+#pragma unroll
+        for (int k = 0; k + 1 < PF; k++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) { nxt[k][s][0] = nxt[k + 1][s][0]; nxt[k][s][1] = nxt[k + 1][s][1]; }
+        if (u + (size_t)PF * stride < nUnits) load_unit(u + (size_t)PF * stride, nxt[PF - 1]);
 
         unsigned s0a = 0, s0b = 0, s1a = 0, s1b = 0;      // row g (c0,c1) and row g+8 (c2,c3), two chains each
 #pragma unroll
@@ -521,16 +528,120 @@ static cudaError_t launch_search_v2(const uint8_t* cur, const uint8_t* refPad, i
     return cudaGetLastError();
 }
 
-static int g_satdCuda = 0;      // tuning/diagnostic: 1 = CUDA-core batch kernel instead of the IMMA one
+// ------------------------------------------------------------------------------------------------
+// Batch on the tensor cores, v2 (shipped): H64 = H2 (x) H32.  The butterfly on sample-index bit 5 pairs sample p
+// with p+32 -- both sit in the same lane (its two 16-byte chunks of a candidate row) -- so it is done first with
+// packed 16-bit adds (VIADD.16x2; int16 wrap is exactly the reference's arithmetic, and only the result mod 2^16
+// matters):  top = x[p] + x[p+32],  bot = x[p] - x[p+32].  The two halves of the coefficient vector are then
+// H32*top and H32*bot: ONE k-step each against the same 32x32 +-1 matrix -> 16 IMMA per 16 candidates instead of
+// 32, and 8 matrix registers instead of 32.  The subtraction is x[p] + ~x[p+32] (= bot - 1 per sample); since
+// H32 * (1,1,...,1) = (32,0,...,0) the missing +1 is a +32 on coefficient 0 of the bottom half, supplied for free
+// through the accumulator input of that MMA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t vadd16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(SATDI_WARPS * 32, MINB)
+satd8x8_imma2_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+
+    // H32 fragments: K position 16r+4q+i <-> sample 8q+4r+i (of the 32 folded samples), column n' = 8t+g
+    uint32_t B[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int pix = 8 * q + 4 * r + i, nn = 8 * t + g;
+                v |= ((__popc(nn & pix) & 1) ? 0xFFu : 0x01u) << (8 * i);
+            }
+            B[t][r] = v;
+        }
+    const int cZero[4] = { 0, 0, 0, 0 };
+    // +32 on bottom-half coefficient 0 (tile 0, column 0 = lanes with q == 0, accumulator slots 0 and 2)
+    const int cFix[4] = { q == 0 ? 32 : 0, 0, q == 0 ? 32 : 0, 0 };
+
+    const size_t nUnits = (n + 15) / 16;
+    const size_t first = (size_t)blockIdx.x * SATDI_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * SATDI_WARPS;
+
+    auto load_unit = [&](size_t u, uint4 (&w)[2][2]) {
+        size_t c0 = u * 16 + g, c1 = c0 + 8;
+        c0 = c0 < n ? c0 : n - 1;
+        c1 = c1 < n ? c1 : n - 1;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            w[s][0] = ld_global_nc(diff + c0 * 64 + 32 * s + 8 * q);
+            w[s][1] = ld_global_nc(diff + c1 * 64 + 32 * s + 8 * q);
+        }
+    };
+
+    uint4 nxt[2][2] = {};
+    if (first < nUnits) load_unit(first, nxt);
+
+    for (size_t u = first; u < nUnits; u += stride) {
+        // fold bit 5, then byte planes.  Fragment registers: [0] row g K 4q+i, [1] row g+8, [2] row g K 16+4q+i, [3] row g+8
+        uint32_t TL[4], TH[4], BLo[4], BHi[4];
+#pragma unroll
+        for (int row = 0; row < 2; row++) {
+            const uint4 a = nxt[0][row], b = nxt[1][row];
+            const uint32_t tx = vadd16x2(a.x, b.x), ty = vadd16x2(a.y, b.y), tz = vadd16x2(a.z, b.z), tw = vadd16x2(a.w, b.w);
+            const uint32_t bx = vadd16x2(a.x, ~b.x), by = vadd16x2(a.y, ~b.y), bz = vadd16x2(a.z, ~b.z), bw = vadd16x2(a.w, ~b.w);
+            TL[row] = prmt(tx, ty, 0x6420);      TH[row] = prmt(tx, ty, 0x7531);
+            TL[2 + row] = prmt(tz, tw, 0x6420);  TH[2 + row] = prmt(tz, tw, 0x7531);
+            BLo[row] = prmt(bx, by, 0x6420);     BHi[row] = prmt(bx, by, 0x7531);
+            BLo[2 + row] = prmt(bz, bw, 0x6420); BHi[2 + row] = prmt(bz, bw, 0x7531);
+        }
+        if (u + stride < nUnits) load_unit(u + stride, nxt);
+
+        unsigned s0a = 0, s0b = 0, s1a = 0, s1b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            int dl[4], dh[4], el[4], eh[4];
+            mma_u8s8(dl, TL, B[t][0], B[t][1], cZero);
+            mma_s8s8(dh, TH, B[t][0], B[t][1], cZero);
+            if (t == 0) mma_u8s8(el, BLo, B[t][0], B[t][1], cFix);
+            else mma_u8s8(el, BLo, B[t][0], B[t][1], cZero);
+            mma_s8s8(eh, BHi, B[t][0], B[t][1], cZero);
+            // lo + 256*hi, sign-extend the low 16 bits (one PRMT with sign replication), |.| accumulate
+            s0a = __sad((int)prmt(dl[0] + dh[0] * 256, 0, 0x9910), 0, s0a); s0b = __sad((int)prmt(dl[1] + dh[1] * 256, 0, 0x9910), 0, s0b);
+            s1a = __sad((int)prmt(dl[2] + dh[2] * 256, 0, 0x9910), 0, s1a); s1b = __sad((int)prmt(dl[3] + dh[3] * 256, 0, 0x9910), 0, s1b);
+            s0a = __sad((int)prmt(el[0] + eh[0] * 256, 0, 0x9910), 0, s0a); s0b = __sad((int)prmt(el[1] + eh[1] * 256, 0, 0x9910), 0, s0b);
+            s1a = __sad((int)prmt(el[2] + eh[2] * 256, 0, 0x9910), 0, s1a); s1b = __sad((int)prmt(el[3] + eh[3] * 256, 0, 0x9910), 0, s1b);
+        }
+        unsigned sad0 = s0a + s0b, sad1 = s1a + s1b;
+        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 1); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 1);
+        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 2); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 2);
+        if (q == 0) {
+            const size_t c0 = u * 16 + g;
+            if (c0 < n) out[c0] = (int)((sad0 + 2) >> 2);
+            if (c0 + 8 < n) out[c0 + 8] = (int)((sad1 + 2) >> 2);
+        }
+    }
+}
+
+static int g_satdCuda = 0;      // tuning/diagnostic: 0 = IMMA v2 (H2 (x) H32 fold, 16 IMMA per unit), 1 = CUDA-core kernel, 2 = IMMA v1 (32 IMMA per unit), 3 = IMMA v2 at 3 CTAs/SM
 void set_satd_cuda_cores(int on) { g_satdCuda = on; }
 
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    if (!g_satdCuda) {
+    if (g_satdCuda != 1) {
         size_t want = ((n + 15) / 16 + SATDI_WARPS - 1) / SATDI_WARPS;
-        size_t cap = (size_t)sm_count() * 2;
-        satd8x8_imma_kernel<<<(int)(want < cap ? want : cap), SATDI_WARPS * 32, 0, st>>>(diff, out, n);
+        size_t cap = (size_t)sm_count() * (g_satdCuda == 3 ? 3 : 2);
+        const int grid = (int)(want < cap ? want : cap);
+        if (g_satdCuda == 2) satd8x8_imma_kernel<2, 1><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
+        else if (g_satdCuda == 3) satd8x8_imma2_kernel<3><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
+        else satd8x8_imma2_kernel<2><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
         count_launch();
         return cudaGetLastError();
     }
