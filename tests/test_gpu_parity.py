@@ -465,3 +465,37 @@ def test_transpose32x32_stage(x266, n):
     assert np.array_equal(y, x.transpose(0, 2, 1))
     if n:
         assert np.array_equal(x266.xTranspose32x32Batch(y), x)
+
+
+# ----------------------------------------------------------------------------- plain-C drop-in proof
+def test_plain_c_bdpi_dropin(x266, ref, tmp_path):
+    """tests/c/bdpi_dropin.c (C only, dlopen): the testbench call sequence gives the same digest through the
+    unmodified reference library and through libx266_b200.so."""
+    import os, subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "bdpi_dropin")
+    subprocess.check_call(["gcc", "-O2", os.path.join(ROOT, "tests", "c", "bdpi_dropin.c"), "-o", exe, "-ldl"])
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libx266ref.so")
+    for seed in ("1", "266"):
+        want = subprocess.check_output([exe, ref_so, seed], text=True).strip()
+        got = subprocess.check_output([exe, x266.LIB_PATH, seed], text=True).strip()
+        assert got == want and len(got) == 16
+
+
+# ------------------------------------------------------------------------------------- error paths
+def test_error_convention(x266):
+    """src/x266.cpp convention: int 0 / -1, no exceptions across the ABI; the binding turns -1 into X266Error."""
+    import torch
+    L = x266.lib()
+    z = np.zeros(2048, np.int16)
+    assert L.xDct32Batch(z.ctypes.data, z.ctypes.data, 2, 0, 11) == -1 and b"xDct32Batch" in L.xGpuLastError()
+    assert L.xDct32Batch(None, None, 1, 4, 11) == -1
+    assert L.xDct32Batch(None, None, 0, 4, 11) == 0                      # empty batch is fine
+    assert L.xDctNBatch(6, z.ctypes.data, z.ctypes.data, 1, 4, 11) == -1
+    d = torch.zeros(4096, dtype=torch.int16, device="cuda")
+    assert L.xDct32BatchDev(d.data_ptr() + 2, d.data_ptr(), 1, 4, 11, None) == -1 and b"alignment" in L.xGpuLastError()
+    with pytest.raises(x266.X266Error):
+        x266.xIntra32Pred(np.zeros((1, 129), np.uint8), np.array([35], np.uint8))
+    with pytest.raises(x266.X266Error):
+        x266.xSatd8x8Search(np.zeros((8, 12), np.uint8), np.zeros((8, 12), np.uint8), 0)     # width not a multiple of 8
+    assert L.xGpuTune(99, 0) == -1

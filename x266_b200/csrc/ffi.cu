@@ -438,7 +438,7 @@ static int search_host(search_launch_t launch, const uint8_t* cur, const uint8_t
 extern "C" int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8_t* dPred, size_t n, void* stream)
 {
     if (n && (!dRefs || !dMode || !dPred)) return fail("xIntra32PredDev", cudaSuccess);
-    if (reinterpret_cast<uintptr_t>(dPred) & 3) return fail("xIntra32PredDev: 4-byte alignment", cudaSuccess);
+    if (reinterpret_cast<uintptr_t>(dPred) & 15) return fail("xIntra32PredDev: 16-byte alignment of pred", cudaSuccess);
     CK(launch_intra32(dRefs, dMode, dPred, n, (cudaStream_t)stream));
     return 0;
 }

@@ -15,6 +15,16 @@ __constant__ int c_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, 
 // 8192/|angle| rounded, for angle = -2,-5,-9,-13,-17,-21,-26,-32
 __constant__ int c_intraInv[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
 
+__device__ __forceinline__ uint32_t intra_row4(uint32_t a, uint32_t b, int f)
+{
+    // 4 pixels: ((32-f)*a + f*b + 16) >> 5 per byte, two 16-bit lanes per multiply-add
+    const uint32_t ae = a & 0x00FF00FFu, ao = (a >> 8) & 0x00FF00FFu;
+    const uint32_t be = b & 0x00FF00FFu, bo = (b >> 8) & 0x00FF00FFu;
+    const uint32_t pe = ((ae * (uint32_t)(32 - f) + be * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
+    const uint32_t po = ((ao * (uint32_t)(32 - f) + bo * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
+    return pe | (po << 8);
+}
+
 // One warp per prediction.  Lane l produces, for it = 0..7, the 4 pixels (row 4*it + (l>>3), columns
 // 4*(l&7) .. +3) and stores them as one 32-bit word: every warp store is 128 contiguous bytes (4 rows).
 // The reference line ref[-32..65] lives in a per-warp shared-memory strip; VER selects which of
@@ -23,43 +33,57 @@ __constant__ int c_intraInv[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
 constexpr int INTRA_WARPS = 8;
 constexpr int INTRA_STRIP = 112;            // 32 (negative part) + 66 + padding, multiple of 16
 
-template <bool VER>
-__device__ __forceinline__ void intra_angular(const uint8_t* __restrict__ ref /* -> ref[0] */, int ang, int lane, uint32_t* out)
+// Angular modes, SWAR: lane l generates, for it = 0,1, the 16 pixels (row 16*it + (l>>1), columns 16*(l&1)..+15) of
+// the vertical-family prediction P_v (distance = row, position along the main reference = column): one (idx, f)
+// pair per row, 5 aligned words of the reference strip re-aligned with funnel shifts, 2 pixels per multiply-add.
+// Vertical modes store the four words directly (512 contiguous bytes per warp store).  Horizontal modes are
+// P_v^T of the left reference: the rows go through a padded per-warp tile and are read back as columns.
+__device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ strip32, int ang, int lane, uint32_t (&w)[2][4])
 {
-    const int rsub = lane >> 3, c0 = (lane & 7) * 4;
 #pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int row = 4 * it + rsub;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int col = c0 + j;
-            const int xr = VER ? col : row;
-            const int yd = VER ? row : col;
-            const int t = (yd + 1) * ang;
-            const int idx = t >> 5, f = t & 31;
-            const int a = ref[xr + idx + 1], b = ref[xr + idx + 2];
-            const int v = ((32 - f) * a + f * b + 16) >> 5;          // f == 0 gives exactly a
-            packed |= (uint32_t)v << (8 * j);
-        }
-        out[it * 32 + lane] = packed;        // word index (4*it + rsub)*8 + (lane&7) == it*32 + lane
+    for (int it = 0; it < 2; it++) {
+        const int row = 16 * it + (lane >> 1), half = lane & 1;
+        const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
+        const int o = 32 + 4 + 16 * half + idx + 1;                 // byte offset of ref[16*half + idx + 1] in the strip
+        const uint32_t* p = strip32 + (o >> 2);
+        const int sh = (o & 3) * 8;
+        const uint32_t x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
+        w[it][0] = intra_row4(__funnelshift_r(x0, x1, sh), __funnelshift_rc(x0, x1, sh + 8), f);
+        w[it][1] = intra_row4(__funnelshift_r(x1, x2, sh), __funnelshift_rc(x1, x2, sh + 8), f);
+        w[it][2] = intra_row4(__funnelshift_r(x2, x3, sh), __funnelshift_rc(x2, x3, sh + 8), f);
+        w[it][3] = intra_row4(__funnelshift_r(x3, x4, sh), __funnelshift_rc(x3, x4, sh + 8), f);
     }
 }
 
 __global__ void __launch_bounds__(INTRA_WARPS * 32)
 intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ modes, uint8_t* __restrict__ pred, size_t n)
 {
-    __shared__ __align__(16) uint8_t strip[INTRA_WARPS][INTRA_STRIP];
+    __shared__ __align__(16) uint8_t strip[INTRA_WARPS][INTRA_STRIP + 16];
     __shared__ __align__(16) uint8_t raw[INTRA_WARPS][144];      // left[64] | top[65]
+    __shared__ __align__(16) uint8_t ttile[INTRA_WARPS][32][36]; // transpose tile for the horizontal modes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* sref = strip[warp] + 32;                            // sref[i] = ref[i], i in -32..65
+    uint8_t* sref = strip[warp] + 32 + 4;                        // sref[i] = ref[i], i in -32..71; sref-32 is word aligned
     uint8_t* sraw = raw[warp];
 
-    for (size_t p = (size_t)blockIdx.x * INTRA_WARPS + warp; p < n; p += (size_t)gridDim.x * INTRA_WARPS) {
-        const int mode = modes[p] > 34 ? 1 : modes[p];           // host API rejects > 34; keep device reads in range
-        const uint8_t* src = refs + p * 129;
+    // software pipeline: the 129 reference bytes and the mode of the NEXT prediction are in flight (registers) while
+    // this one is generated -- otherwise every prediction pays a full DRAM latency with nothing to overlap it
+    const size_t pstride = (size_t)gridDim.x * INTRA_WARPS;
+    uint8_t nraw[5] = {};
+    int nmode = 1;
+    auto prefetch = [&](size_t q) {
+        const uint8_t* src = refs + q * 129;
 #pragma unroll
-        for (int i = lane; i < 129; i += 32) sraw[i] = src[i];
+        for (int k = 0; k < 5; k++) { const int i = lane + 32 * k; if (i < 129) nraw[k] = src[i]; }
+        nmode = modes[q];
+    };
+    const size_t p0 = (size_t)blockIdx.x * INTRA_WARPS + warp;
+    if (p0 < n) prefetch(p0);
+
+    for (size_t p = p0; p < n; p += pstride) {
+        const int mode = nmode > 34 ? 1 : nmode;                 // host API rejects > 34; keep device reads in range
+#pragma unroll
+        for (int k = 0; k < 5; k++) { const int i = lane + 32 * k; if (i < 129) sraw[i] = nraw[k]; }
+        if (p + pstride < n) prefetch(p + pstride);
         __syncwarp();
         const uint8_t* left = sraw;          // left[i] = pixel (-1, i)
         const uint8_t* top = sraw + 64;      // top[0] = corner, top[1+i] = pixel (i, -1)
@@ -69,7 +93,7 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
 
         if (mode >= 2) {
 #pragma unroll
-            for (int i = lane; i <= 65; i += 32) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
+            for (int i = lane; i <= 71; i += 32) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
             if (ang < 0) {
                 int inv = 0;
 #pragma unroll
@@ -81,8 +105,30 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
                 }
             }
             __syncwarp();
-            if (isVer) intra_angular<true>(sref, ang, lane, out);
-            else intra_angular<false>(sref, ang, lane, out);
+            uint32_t w[2][4];
+            intra_angular_rows(reinterpret_cast<const uint32_t*>(strip[warp]), ang, lane, w);
+            if (isVer) {
+#pragma unroll
+                for (int it = 0; it < 2; it++)
+                    reinterpret_cast<uint4*>(out)[it * 32 + lane] = make_uint4(w[it][0], w[it][1], w[it][2], w[it][3]);
+            } else {
+#pragma unroll
+                for (int it = 0; it < 2; it++) {
+                    uint32_t* trow = reinterpret_cast<uint32_t*>(&ttile[warp][16 * it + (lane >> 1)][16 * (lane & 1)]);
+                    trow[0] = w[it][0]; trow[1] = w[it][1]; trow[2] = w[it][2]; trow[3] = w[it][3];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 2; it++) {
+                    const int r = 16 * it + (lane >> 1), c0 = 16 * (lane & 1);          // output row r, columns c0..c0+15 = P_v[c][r]
+                    uint32_t o4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        o4[k] = ttile[warp][c0 + 4 * k][r] | (ttile[warp][c0 + 4 * k + 1][r] << 8) |
+                                (ttile[warp][c0 + 4 * k + 2][r] << 16) | ((uint32_t)ttile[warp][c0 + 4 * k + 3][r] << 24);
+                    reinterpret_cast<uint4*>(out)[it * 32 + lane] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                }
+            }
         } else if (mode == 1) {
             int s = left[lane] + top[1 + lane];
 #pragma unroll
@@ -239,16 +285,6 @@ intra32_decide_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
 // symmetric), so one SWAR row generator (8 pixels of one prediction row = one A-fragment register pair,
 // 2 pixels per 32-bit multiply-add) serves all 33 angular modes.  One warp owns one mode at a time.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t intra_row4(uint32_t a, uint32_t b, int f)
-{
-    // 4 pixels: ((32-f)*a + f*b + 16) >> 5 per byte, two 16-bit lanes per multiply-add
-    const uint32_t ae = a & 0x00FF00FFu, ao = (a >> 8) & 0x00FF00FFu;
-    const uint32_t be = b & 0x00FF00FFu, bo = (b >> 8) & 0x00FF00FFu;
-    const uint32_t pe = ((ae * (uint32_t)(32 - f) + be * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
-    const uint32_t po = ((ao * (uint32_t)(32 - f) + bo * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
-    return pe | (po << 8);
-}
-
 __global__ void __launch_bounds__(IDEC_WARPS * 32, 2)
 intra32_decide_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refs, uint32_t* __restrict__ cost,
                          int32_t* __restrict__ bestMode, size_t n)
