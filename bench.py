@@ -117,6 +117,24 @@ def cpu_reference_rate(n_blocks, threads, reps=1, data=None):
     return n_blocks / best, kind, x, y
 
 
+def cpu_reference_o3_rate(n_blocks, threads):
+    """Second row of BASELINE.md section 2: the same reference C built with -O3 -march=native (built where the
+    reference tree lives; the GPU box may have another CPU, so it runs in a subprocess and may legitimately fail)."""
+    code = (
+        "import sys, time; sys.path.insert(0, %r)\n"
+        "from oracle import Oracle, Ref\n"
+        "o = Oracle(); r = Ref('o3'); x = o.residual(%d * 1024, 266, 1).reshape(-1, 32, 32)\n"
+        "best = 1e9\n"
+        "for _ in range(2):\n"
+        "    t = time.perf_counter(); r.dct32(x, %d, %d, threads=%d); best = min(best, time.perf_counter() - t)\n"
+        "print(%d / best)\n" % (ROOT, n_blocks, SHIFTS[0], SHIFTS[1], threads, n_blocks))
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+        return float(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else None
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -315,6 +333,17 @@ def main():
         ms = timed(lambda: xb.xIntra32PredDev(refs.data_ptr(), modes.data_ptr(), pred.data_ptr(), npred, st), 10)
         hbm("intra32_predictions_per_s", npred, 1154, ms, "parity unpinned (no C model in the reference)")
         del refs, modes, pred
+        if world > 1:
+            # optional frame re-assembly: every rank contributes one 8K frame of coefficients (66 MB) and
+            # receives all of them -- the only collective in the repo, off the hot path, NCCL over NVLink/NVSwitch
+            slab = dst[:BLOCKS_PER_FRAME].reshape(-1)
+            full = torch.empty(world * slab.numel(), dtype=slab.dtype, device=dev)
+            ms = timed(lambda: dist.all_gather_into_tensor(full, slab), 10)
+            ok = bool(torch.equal(full[rank * slab.numel():(rank + 1) * slab.numel()], slab))
+            secondary.append({"metric": "coef_frame_allgather_GBps_per_rank", "value": (world - 1) * slab.numel() * 2 / (ms * 1e-3) / 1e9,
+                              "n_gpus": world, "ms": ms, "config": "ncclAllGather of one 8K coefficient frame per rank (optional re-assembly, not on the hot path)",
+                              "own_slab_intact": ok, "roofline": {"bound": "nvlink", "achieved": (world - 1) * slab.numel() * 2 / (ms * 1e-3) / 1e9,
+                                                                  "peak": 770.0, "unit": "GB/s", "frac": (world - 1) * slab.numel() * 2 / (ms * 1e-3) / 1e9 / 770.0, "traffic": None}})
 
     # ---- CPU baseline: the reference C on this box's host cores, bounded sample, rank 0 at N=1 only
     cpu = None
@@ -326,7 +355,8 @@ def main():
         parity = bool(np.array_equal(y.reshape(-1), gpu_sample))
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"{args.cpu_frames} frames ({n_cpu} blocks) of the workload, gcc -O2, best of 2",
-               "single_thread_value": rate1, "gpu_output_bit_exact_on_sample": parity}
+               "single_thread_value": rate1, "o3_march_native_value": cpu_reference_o3_rate(n_cpu, threads),
+               "gpu_output_bit_exact_on_sample": parity}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
