@@ -24,15 +24,15 @@ xb.tune(0, -1); xb.set_dct_variant(xb.DCT_AUTO)
 for log2n, sh in ((2, (1, 8)), (3, (2, 9)), (4, (3, 10))):
     n = 1 << log2n
     xs = o.residual(1237 * n * n, 2, 2)
-    for cc in (0, 1):
+    for cc in (0, 1, 2):
         xb.tune(3, cc)
         check(f"dct{n} cuda_core={cc}", np.array_equal(xb.xDctNBatch(log2n, xs, *sh), o.dct(xs.reshape(-1, n, n), log2n, *sh).ravel()))
 xb.tune(3, 0)
 check("partialButterfly32", np.array_equal(xb.partialButterfly32(x[:77 * 32], 4, 77), o.partial(x[:77 * 32], 4, 77)))
 d = o.residual(1003 * 64, 3, 2)
-for v in (0, 1):
+for v in (0, 1, 2, 3):
     xb.tune(2, v)
-    check(f"satd batch cuda_core={v}", np.array_equal(xb.xSatd8x8Batch(d), o.satd(d)))
+    check(f"satd batch variant={v}", np.array_equal(xb.xSatd8x8Batch(d), o.satd(d)))
 xb.tune(2, 0)
 rng = np.random.default_rng(0)
 for R, (w, h) in ((3, (40, 24)), (8, (200, 24)), (32, (200, 16))):
@@ -52,5 +52,22 @@ w, h = 96, 64
 fr = lambda: o.conv_input_fmt(rng.integers(0, 256, (h, w)).astype(np.uint8), rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8), rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8))
 a, b = fr(), fr()
 check("frame resi dct32", np.array_equal(xb.xFrameResiDct32(a, b, w, h, 4, 11), o.frame_resi_dct32(a, b, w, h, 4, 11)))
+ci = o.residual(9 * 1024, 5, 2).reshape(-1, 32, 32)
+check("idct32", np.array_equal(xb.xIdct32Batch(ci, 7, 12), o.idct(ci, 5, 7, 12)))
+cb = rng.integers(0, 256, (6, 32, 32)).astype(np.uint8)
+rb = rng.integers(0, 256, (6, 129)).astype(np.uint8)
+for v1 in (0, 1):
+    xb.tune(5, v1)
+    cst, bst = xb.xIntra32Decide(cb, rb)
+    check(f"intra decide v1={v1}", all(np.array_equal(cst[i], o.intra32_decide(cb[i], rb[i, :64], rb[i, 64:])[0]) for i in range(6)))
+xb.tune(5, 0)
+tt = rng.integers(0, 256, (11, 32, 32)).astype(np.uint8)
+check("transpose32", np.array_equal(xb.xTranspose32x32Batch(tt), tt.transpose(0, 2, 1)))
+sa, sb2 = rng.integers(0, 256, (65, 65)).astype(np.uint8), rng.integers(0, 256, (65, 65)).astype(np.uint8)
+check("sad region", xb.sad(sa, sb2) == o.sad(sa, sb2))
+scur = rng.integers(0, 256, (24, 40)).astype(np.uint8); sref = rng.integers(0, 256, (24 + 16, 40 + 16)).astype(np.uint8)
+c, b = xb.xSad8x8Search(scur, sref, 8)
+wc, wb = o.sad_search(scur, sref, 8, 0, 15)
+check("sad search", np.array_equal(c, wc) and np.array_equal(b, wb))
 print("ALL OK" if ok else "SOME FAILED")
 sys.exit(0 if ok else 1)

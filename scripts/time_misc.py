@@ -23,6 +23,10 @@ for log2n, (s1, s2) in ((2, (1, 8)), (3, (2, 9)), (4, (3, 10)), (5, (4, 11))):
 nb32 = nsamp >> 10
 ms = timeit(lambda: xb.xIdct32BatchDev(src.data_ptr(), dst.data_ptr(), nb32, 7, 12, st))
 print(f"idct32: {ms:7.3f} ms  {nb32 / ms / 1e6:9.2f} G blocks/s  {nsamp * 4 / ms / 1e6:7.0f} GB/s  {nsamp * 4 / ms / 1e6 / 6545.6 * 100:5.1f}% of measured HBM", flush=True)
+xb.tune(3, 2)
+ms = timeit(lambda: xb.xDctNBatchDev(2, src.data_ptr(), dst.data_ptr(), nsamp >> 4, 1, 8, st))
+print(f"dct4 one-block-per-thread: {ms:7.3f} ms  {nsamp * 4 / ms / 1e6:7.0f} GB/s  {nsamp * 4 / ms / 1e6 / 6545.6 * 100:5.1f}% of measured HBM", flush=True)
+xb.tune(3, 0)
 line = 1 << 22
 ms = timeit(lambda: xb.xPartialButterfly32Dev(src.data_ptr(), dst.data_ptr(), 4, line, st))
 print(f"partialButterfly32 line={line}: {ms:7.3f} ms  {line * 128 / ms / 1e6:7.0f} GB/s", flush=True)

@@ -148,7 +148,7 @@ def test_bdpi_stream_against_live_reference(x266, ref):
 # ------------------------------------------------------------------------------------ DCT N<32
 @pytest.mark.parametrize("log2n", [2, 3, 4])
 @pytest.mark.parametrize("nblk", [1, 2, 3, 4, 5, 64, 1000, 4097, 75777])
-@pytest.mark.parametrize("cuda_core", [0, 1])
+@pytest.mark.parametrize("cuda_core", [0, 1, 2])
 def test_dctN(x266, orc, log2n, nblk, cuda_core):
     """N<32: tensor-core kernels where they exist (tune 3 = 0) and the CUDA-core dctN kernels (tune 3 = 1)"""
     n = 1 << log2n

@@ -246,6 +246,88 @@ dct4_reg_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size
 }
 
 // ------------------------------------------------------------------------------------------------
+// 4x4 blocks, fully coalesced variant: a warp moves 2 KiB (64 blocks) per iteration with four 512-byte
+// load instructions; lane pairs then swap 16-byte halves (8 SHFL) so that every lane owns two whole blocks,
+// transforms them in registers, swaps the halves back (8 SHFL) and stores with four 512-byte instructions.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dct4_block(const uint32_t (&w)[8], uint32_t (&o)[8], int add1, int shift1, int add2, int shift2)
+{
+    int c[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int x[4], y[4];
+        x[0] = (int)(short)(w[2 * j] & 0xFFFF); x[1] = (int)w[2 * j] >> 16;
+        x[2] = (int)(short)(w[2 * j + 1] & 0xFFFF); x[3] = (int)w[2 * j + 1] >> 16;
+        Dct1D<4, 1, 4>::run(x, y);
+#pragma unroll
+        for (int k = 0; k < 4; k++) c[k][j] = (int)(short)((y[k] + add1) >> shift1);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int y[4];
+        Dct1D<4, 1, 4>::run(c[k], y);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) c[k][k2] = (y[k2] + add2) >> shift2;
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) {
+        o[2 * k2] = prmt((uint32_t)c[0][k2], (uint32_t)c[1][k2], 0x5410);
+        o[2 * k2 + 1] = prmt((uint32_t)c[2][k2], (uint32_t)c[3][k2], 0x5410);
+    }
+}
+
+__device__ __forceinline__ uint4 shfl_xor1(uint4 v)
+{
+    v.x = __shfl_xor_sync(0xffffffffu, v.x, 1); v.y = __shfl_xor_sync(0xffffffffu, v.y, 1);
+    v.z = __shfl_xor_sync(0xffffffffu, v.z, 1); v.w = __shfl_xor_sync(0xffffffffu, v.w, 1);
+    return v;
+}
+
+constexpr int DCT4X_WARPS = 8;
+
+__global__ void __launch_bounds__(DCT4X_WARPS * 32)
+dct4_xchg_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool odd = lane & 1;
+    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
+    const size_t nPieces = nBlocks * 2;                       // 16-byte pieces
+    const size_t nUnits = (nPieces + 127) / 128;
+    for (size_t u = (size_t)blockIdx.x * DCT4X_WARPS + warp; u < nUnits; u += (size_t)gridDim.x * DCT4X_WARPS) {
+        const size_t base = u * 128;                          // piece index of this unit
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            size_t pc = base + j * 32 + lane;
+            pc = pc < nPieces ? pc : nPieces - 1;             // ragged tail: clamp (never stored)
+            v[j] = ld_global_stream(src + pc * 8);
+        }
+        // even lanes own the blocks of j = 0,1, odd lanes those of j = 2,3
+        const uint4 r0 = shfl_xor1(odd ? v[0] : v[2]);
+        const uint4 r1 = shfl_xor1(odd ? v[1] : v[3]);
+        const uint4 a0 = odd ? r0 : v[0], a1 = odd ? v[2] : r0;       // block A: halves 0,1
+        const uint4 b0 = odd ? r1 : v[1], b1 = odd ? v[3] : r1;       // block B
+        const uint32_t wa[8] = { a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w };
+        const uint32_t wb[8] = { b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w };
+        uint32_t oa[8], ob[8];
+        dct4_block(wa, oa, add1, shift1, add2, shift2);
+        dct4_block(wb, ob, add1, shift1, add2, shift2);
+        const uint4 A0 = make_uint4(oa[0], oa[1], oa[2], oa[3]), A1 = make_uint4(oa[4], oa[5], oa[6], oa[7]);
+        const uint4 B0 = make_uint4(ob[0], ob[1], ob[2], ob[3]), B1 = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+        // even lane keeps halves 0 of its blocks and receives the odd lane's halves 0; odd keeps halves 1
+        const uint4 s0 = shfl_xor1(odd ? A0 : A1);
+        const uint4 s1 = shfl_xor1(odd ? B0 : B1);
+        uint4 o[4];
+        o[0] = odd ? s0 : A0;  o[1] = odd ? s1 : B0;  o[2] = odd ? A1 : s0;  o[3] = odd ? B1 : s1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const size_t pc = base + j * 32 + lane;
+            if (pc < nPieces) st_global_stream(dst + pc * 8, o[j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static int grid_for(size_t units, int unitsPerCta, int ctasPerSm)
@@ -272,15 +354,20 @@ cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int li
     return cudaGetLastError();
 }
 
-static int g_smallCuda = 0;
+static int g_smallCuda = 0;     // 0: shipped (IMMA for N=8,16; lane-exchange kernel for N=4); 1: smem-staged dctN kernels; 2: N=4 one block per thread
 void set_small_dct_cuda_cores(int on) { g_smallCuda = on; }
 
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
 {
     if (nBlocks == 0) return cudaSuccess;
-    if (log2n == 4 && !g_smallCuda) return launch_dct16_imma(src, dst, nBlocks, s1, s2, st);
-    if (log2n == 3 && !g_smallCuda) return launch_dct8_imma(src, dst, nBlocks, s1, s2, st);
-    if (log2n == 2 && !g_smallCuda) {
+    if (log2n == 4 && g_smallCuda != 1) return launch_dct16_imma(src, dst, nBlocks, s1, s2, st);
+    if (log2n == 3 && g_smallCuda != 1) return launch_dct8_imma(src, dst, nBlocks, s1, s2, st);
+    if (log2n == 2 && g_smallCuda == 0) {
+        dct4_xchg_kernel<<<grid_for((nBlocks + 63) / 64, DCT4X_WARPS, 8), DCT4X_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
+        count_launch();
+        return cudaGetLastError();
+    }
+    if (log2n == 2 && g_smallCuda == 2) {
         dct4_reg_kernel<<<grid_for(nBlocks, 256, 8), 256, 0, st>>>(src, dst, nBlocks, s1, s2);
         count_launch();
         return cudaGetLastError();
