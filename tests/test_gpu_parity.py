@@ -220,9 +220,10 @@ def make_frames(w, h, rng_px, seed=266):
 
 
 @pytest.mark.parametrize("rng_px", [0, 3, 8, 16, 32])
-@pytest.mark.parametrize("v1", [0, 1])
+@pytest.mark.parametrize("v1", [0, 1, 2])
 def test_satd_search_small(x266, orc, rng_px, v1):
-    """both search kernels (v1: CTA per block; v2: transform-domain strips, R in {8,16,32})"""
+    """all search kernels (0: v3 packed transform domain, two positions per thread; 1: v1 CTA per block;
+    2: v2 transform-domain strips; v2/v3 exist for R in {8,16,32}, other ranges take v1)"""
     x266.tune(1, v1)
     cur, refp = make_frames(64, 48, rng_px)
     cost, best = x266.xSatd8x8Search(cur, refp, rng_px)
@@ -250,6 +251,27 @@ def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px):
     flatp = np.full((24 + 2 * rng_px, 200 + 2 * rng_px), 10, np.uint8)
     c, b = x266.xSatd8x8Search(flat, flatp, rng_px)
     assert (b[:, 1] == 0).all() and (b[:, 2] == 0).all() and (c == c[0, 0, 0]).all()
+
+
+@pytest.mark.parametrize("rng_px", [8, 16, 32])
+def test_satd_search_extreme_patterns(x266, orc, rng_px):
+    """v3 keeps two biased coefficients per 32-bit word: frames built from the 64 Hadamard basis patterns (pixels
+    0/255, every coefficient driven to +-8160 / 16320) and from random 0/255 pixels must not carry between halves."""
+    r = np.random.default_rng(11)
+    H = np.array([[(-1) ** bin(a & b).count("1") for b in range(64)] for a in range(64)])
+    w, h = 256, 32
+    cur = np.zeros((h, w), np.uint8)
+    ref = np.zeros((h, w), np.uint8)
+    for by in range(h // 8):
+        for bx in range(w // 8):
+            k = int(r.integers(0, 64))
+            cur[by * 8:by * 8 + 8, bx * 8:bx * 8 + 8] = np.where(H[k] > 0, 255, 0).reshape(8, 8)
+            ref[by * 8:by * 8 + 8, bx * 8:bx * 8 + 8] = np.where(H[k] > 0, 0, 255).reshape(8, 8)
+    for c, f in ((cur, np.pad(ref, rng_px, mode="edge")),
+                 (r.choice([0, 255], (h, w)).astype(np.uint8), r.choice([0, 255], (h + 2 * rng_px, w + 2 * rng_px)).astype(np.uint8))):
+        cost, best = x266.xSatd8x8Search(c, f, rng_px)
+        wc, wb = orc.satd_search(c, f, rng_px, 0, (w // 8) * (h // 8))
+        assert np.array_equal(cost, wc) and np.array_equal(best, wb)
 
 
 def test_satd_search_1080p_sample(x266, orc):

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 SHIFTS = {4: (1, 8), 8: (2, 9), 16: (3, 10), 32: (4, 11)}     # src/mkDct32.bsv:93-98
 
@@ -220,3 +220,28 @@ def test_frame_residual_dct_oracle_composition(orc):
     resi = planes[0].astype(np.int16) - planes2[0].astype(np.int16)
     blocks = resi.reshape(h // 32, 32, w // 32, 32).transpose(0, 2, 1, 3).reshape(-1, 32, 32)
     assert (got == orc.dct(blocks, 5, 4, 11)).all()
+
+
+def test_packed_search_arithmetic_model(orc, tmp_path):
+    """The search kernel v3 computes SATD from packed, biased 16-bit transforms of the two pixel blocks
+    (x266_b200/csrc/satd_packed.h).  The same inline functions, compiled by g++, must reproduce satd8x8 of the
+    difference for random blocks and for blocks that drive every coefficient to its extreme, and no packed half
+    may exceed 16352 (so four of them still add up inside 16 bits)."""
+    import ctypes
+    import subprocess
+    so = str(tmp_path / "satd_packed_model.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "c", "satd_packed_model.cpp")])
+    L = ctypes.CDLL(so)
+    r = np.random.default_rng(0)
+    H = np.array([[(-1) ** bin(a & b).count("1") for b in range(64)] for a in range(64)])
+    pats = np.array([np.where(H[k] > 0, hi, 255 - hi) for k in range(64) for hi in (255, 0)], dtype=np.uint8)
+    cur = np.concatenate([r.integers(0, 256, (20000, 64)), np.repeat(pats, 128, axis=0), r.choice([0, 255], (20000, 64))]).astype(np.uint8)
+    ref = np.concatenate([r.integers(0, 256, (20000, 64)), np.tile(pats, (128, 1)), r.choice([0, 255], (20000, 64))]).astype(np.uint8)
+    cur, ref = np.ascontiguousarray(cur), np.ascontiguousarray(ref)
+    cost = np.zeros(cur.shape[0], np.int32)
+    worst = ctypes.c_uint32()
+    L.packed_satd(cur.ctypes.data_as(ctypes.c_void_p), ref.ctypes.data_as(ctypes.c_void_p), cur.shape[0],
+                  cost.ctypes.data_as(ctypes.c_void_p), ctypes.byref(worst))
+    want = orc.satd((cur.astype(np.int16) - ref.astype(np.int16)).reshape(-1))
+    assert np.array_equal(cost, want)
+    assert worst.value == 16352

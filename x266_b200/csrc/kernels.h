@@ -18,7 +18,7 @@ void set_small_dct_cuda_cores(int on);   // tuning/diagnostic: CUDA-core dctN ke
 void set_imma_config(int id);   // tuning/diagnostic: selects a (warps, stages, CTAs/SM, staging) instantiation
 void set_satd_cuda_cores(int on);   // tuning/diagnostic: CUDA-core SATD batch kernel instead of IMMA
 void set_decide_v1(int on);     // tuning/diagnostic: CUDA-core intra decision kernel instead of the tensor-core one
-void set_search_v1(int on);     // tuning/diagnostic: force the v1 (one CTA per block) search kernel
+void set_search_v1(int on);     // tuning/diagnostic: 0 = v3 (default), 1 = v1 (one CTA per block), 2/3 = v2 (strips)
 cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int line, cudaStream_t st);
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 
@@ -32,6 +32,8 @@ cudaError_t launch_conv_output420(const uint8_t* tiles, uint8_t* Y, intptr_t str
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st);
 cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                   size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
+cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                     size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
 cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st);
 cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, unsigned* out, cudaStream_t st);
 cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,

@@ -508,7 +508,7 @@ satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     }
 }
 
-static int g_searchV1 = 0;      // 0: v2, 2 CTAs/SM register budget; 1: v1; 2: v2 squeezed to 3 CTAs/SM
+static int g_searchV1 = 0;      // 0: v3 (satd_search3.cu); 1: v1; 2: v2 squeezed to 3 CTAs/SM; 3: v2, 2 CTAs/SM
 void set_search_v1(int on) { g_searchV1 = on; }
 
 template <int R>
@@ -665,6 +665,8 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
 {
     if (blk1 <= blk0) return cudaSuccess;
     if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
+    if (g_searchV1 == 0 && (range == 32 || range == 16 || range == 8))
+        return launch_satd8x8_search_v3(cur, refPad, strd, w, h, range, blk0, blk1, cost, best, st);
     if (g_searchV1 != 1) {
         if (range == 32) return launch_search_v2<32>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
         if (range == 16) return launch_search_v2<16>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);

@@ -1,0 +1,260 @@
+// satd_search3.cu -- SATD full search v3 (R in {8,16,32}): packed 16-bit transform domain, two positions per thread.
+//
+// Reference behaviour: cost of one candidate = satd8x8(cur - ref(mv)), src_tb/satd.c:31-118.  The search loop,
+// window convention and argmin rule are ours (the reference has no search loop).
+//
+// Why a third kernel: v2 (satd.cu) is bound by the shared-memory return path -- every candidate re-reads the 64
+// 32-bit coefficients of T(cur) (256 B, 16 LDS.128 per warp = 64 SM cycles per 32 candidates) -- and not by HBM or
+// the ALUs (ncu: issue slots 54 % busy).  v3 removes three quarters of that traffic and a third of the instructions:
+//   * coefficients are packed two per word with a bias that keeps every half non-negative (satd_packed.h), so
+//     T(cur) is 128 B and every butterfly of the transform is ONE plain 32-bit add for two coefficients;
+//   * a thread owns TWO window positions (p, p+8) that share 8 of their 9 blocks, so one T(cur) word fetched
+//     from shared memory serves two candidates: 64 B of shared-memory traffic per candidate instead of 256;
+//   * |a-b| = 2 max(a,b) - a - b with sum_k T[k] = 64 x[0][0]: per pair of coefficients one VIMNMX.S16x2, a
+//     quarter of an add and an eighth of an IDP.2A, instead of two VABSDIFF.
+// Work decomposition: one CTA per (row of 8x8 blocks, tile of 64 horizontal window positions); the tile's window
+// (2R+8 rows x 72 bytes) and the T(cur) of the R/4+8 blocks it can serve live in shared memory; the CTA's warps
+// split the 2R+1 vertical offsets and otherwise run on their own.  Lane (g, e) = (lane>>3, lane&7) owns positions
+// P0+16g+e and P0+16g+8+e; with q = P0/8+2g the blocks of "slot" s are i = q-R/4+s for both positions
+// (mx = e+2R-8s and e+2R+8-8s), so the eight lanes of a group read the same T(cur) and write 32 contiguous bytes
+// of the cost surface.  Tiles follow window positions, not blocks, so no lane is wasted on a strip edge (v2: 38 %).
+// A block's candidates span up to three tiles: the argmin is combined with 64-bit atomicMin keys
+// (cost, mvx^2+mvy^2, my, mx) in a stream-ordered scratch buffer and decoded by a second tiny kernel.
+#include "common.cuh"
+#include "kernels.h"
+#include "satd_packed.h"
+
+namespace x266 {
+
+constexpr int S3_WARPS = 5;
+constexpr int S3_TILE = 64;                  // window positions per CTA
+constexpr int S3_WP = 72;                    // window pitch in bytes: 64 positions + 7 halo columns (+1)
+constexpr int S3_TCS = 36;                   // T(cur) row: 32 words + 64*cur[0][0] + pad (16-byte rows, distinct banks for 4 blocks)
+
+template <int R>
+__global__ void __launch_bounds__(S3_WARPS * 32, 3)
+satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w, int by0,
+                         size_t blk0, size_t blk1, uint32_t* __restrict__ cost, unsigned long long* __restrict__ keys)
+{
+    constexpr int SIDE = 2 * R + 1;
+    constexpr int WS = 2 * R + 8;
+    constexpr int NSLOT = R / 4 + 2;
+    constexpr int NBLK = R / 4 + 8;
+    constexpr int NT = S3_WARPS * 32;
+    __shared__ __align__(16) uint8_t win[WS * S3_WP];
+    __shared__ __align__(16) uint8_t curw[8][128];
+    __shared__ __align__(16) uint32_t Vt[S3_WARPS][S3_WP][4];
+    __shared__ __align__(16) uint32_t tcur[NBLK][S3_TCS];
+    __shared__ unsigned long long sBest[NBLK];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 3, e = lane & 7;
+    const int bw = w >> 3;
+    const int by8 = by0 + blockIdx.y;
+    const int P0 = blockIdx.x * S3_TILE;
+    const int iBase = P0 / 8 - R / 4;
+    const size_t bRow = (size_t)by8 * bw;
+    {
+        const int lo = iBase < 0 ? 0 : iBase;
+        const int hi = (iBase + NBLK - 1) < (bw - 1) ? (iBase + NBLK - 1) : (bw - 1);
+        if (hi < lo || bRow + hi < blk0 || bRow + lo >= blk1) return;
+    }
+
+    // ---- stage the window, the current blocks and T(cur)
+    const int padW = w + 2 * R;
+    const uint8_t* wsrc = refPad + (intptr_t)by8 * 8 * strd + P0;
+    for (int idx = tid; idx < WS * S3_WP; idx += NT) {
+        const int yy = idx / S3_WP, xx = idx - yy * S3_WP;
+        win[idx] = (P0 + xx < padW) ? wsrc[(intptr_t)yy * strd + xx] : (uint8_t)0;
+    }
+    for (int idx = tid; idx < 8 * 128; idx += NT) {
+        const int r = idx >> 7, x = idx & 127;
+        const int i = iBase + (x >> 3);
+        curw[r][x] = (x < NBLK * 8 && i >= 0 && i < bw) ? cur[(size_t)(by8 * 8 + r) * w + i * 8 + (x & 7)] : (uint8_t)0;
+    }
+    if (tid < NBLK) sBest[tid] = ~0ull;
+    __syncthreads();
+    if (warp * 8 < NBLK) {                       // warp k transforms blocks 8k .. 8k+7 with the code path of the window
+        if (lane < 16) {
+            uint32_t px[8], o[4][4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) px[i] = *reinterpret_cast<const uint32_t*>(&curw[i][64 * warp + 4 * lane]);
+            s3::vertical4(px, o);
+#pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(Vt[warp][4 * lane + c]) = make_uint4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        }
+        __syncwarp();
+        if (lane < 8 && warp * 8 + lane < NBLK) {
+            uint32_t T[32];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(Vt[warp][8 * lane + c]);
+                T[c] = v.x; T[8 + c] = v.y; T[16 + c] = v.z; T[24 + c] = v.w;
+            }
+            s3::horizontal8(T);
+            uint32_t* d = tcur[warp * 8 + lane];
+#pragma unroll
+            for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(d + 4 * k) = make_uint4(T[4 * k], T[4 * k + 1], T[4 * k + 2], T[4 * k + 3]);
+            d[32] = 64u * curw[0][64 * warp + 8 * lane];
+        }
+    }
+    __syncthreads();
+
+    // ---- main loop: this warp's vertical offsets
+    const int xa = 16 * g + e;                   // tile-local column of position A; B = A + 8
+    const int iq = P0 / 8 + 2 * g - R / 4;       // block of slot 0
+    unsigned keyA[NSLOT], keyB[NSLOT];           // per (slot, position): cost << 7 | rank(my); mx is fixed per entry
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) keyA[s] = keyB[s] = 0xFFFFFFFFu;
+    uint32_t (*V)[4] = Vt[warp];
+
+    for (int my = warp; my < SIDE; my += S3_WARPS) {
+        if (lane < S3_WP / 4) {
+            uint32_t px[8], o[4][4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) px[i] = *reinterpret_cast<const uint32_t*>(&win[(my + i) * S3_WP + 4 * lane]);
+            s3::vertical4(px, o);
+#pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(V[4 * lane + c]) = make_uint4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        }
+        __syncwarp();
+        uint32_t TA[32], TB[32];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint4 a = *reinterpret_cast<const uint4*>(V[xa + c]);
+            const uint4 b = *reinterpret_cast<const uint4*>(V[xa + 8 + c]);
+            TA[c] = a.x; TA[8 + c] = a.y; TA[16 + c] = a.z; TA[24 + c] = a.w;
+            TB[c] = b.x; TB[8 + c] = b.y; TB[16 + c] = b.z; TB[24 + c] = b.w;
+        }
+        __syncwarp();                            // V may be overwritten by the next iteration from here on
+        s3::horizontal8(TA);
+        s3::horizontal8(TB);
+        // cost = (2*acc - 64*ref[0][0] - 64*cur[0][0] - 2*BIAS_SUM + 2) >> 2
+        const uint32_t subA = 64u * win[my * S3_WP + xa] + 2u * s3::BIAS_SUM - 2u;
+        const uint32_t subB = 64u * win[my * S3_WP + xa + 8] + 2u * s3::BIAS_SUM - 2u;
+        const int dy = my - R;
+        const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
+        // cost index of (slot s, position A) = cbase + s * (SIDE*SIDE - 8); position B: + 8
+        uint32_t* cbase = cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R;
+
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) {
+            const int i = iq + s;
+            const size_t b = bRow + i;
+            if (i >= 0 && i < bw && b >= blk0 && b < blk1) {
+                const bool doA = (s <= R / 4) && (s >= 1 || e == 0);
+                const bool doB = (s >= 1) && (s >= 2 || e == 0);
+                const uint32_t* tc = tcur[2 * g + s];
+                uint32_t accA = 0, accB = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint4 c = *reinterpret_cast<const uint4*>(tc + 4 * k);
+                    if (s <= R / 4) {
+                        const uint32_t m = (s3::vmax2(TA[4 * k], c.x) + s3::vmax2(TA[4 * k + 1], c.y)) +
+                                           (s3::vmax2(TA[4 * k + 2], c.z) + s3::vmax2(TA[4 * k + 3], c.w));
+                        accA = s3::fold2(m, accA);
+                    }
+                    if (s >= 1) {
+                        const uint32_t m = (s3::vmax2(TB[4 * k], c.x) + s3::vmax2(TB[4 * k + 1], c.y)) +
+                                           (s3::vmax2(TB[4 * k + 2], c.z) + s3::vmax2(TB[4 * k + 3], c.w));
+                        accB = s3::fold2(m, accB);
+                    }
+                }
+                const uint32_t c64 = tc[32];
+                if (doA) {
+                    const uint32_t c4 = (2u * accA - subA - c64) >> 2;
+                    if (cost) cbase[s * (SIDE * SIDE - 8)] = c4;
+                    const unsigned key = (c4 << 7) | rank;
+                    keyA[s] = key < keyA[s] ? key : keyA[s];
+                }
+                if (doB) {
+                    const uint32_t c4 = (2u * accB - subB - c64) >> 2;
+                    if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = c4;
+                    const unsigned key = (c4 << 7) | rank;
+                    keyB[s] = key < keyB[s] ? key : keyB[s];
+                }
+            }
+        }
+    }
+
+    // ---- argmin: per (slot, position) the best my is known; fold the 8 lanes of a group, then the CTA, then the frame
+    if (keys) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) {
+#pragma unroll
+            for (int ab = 0; ab < 2; ab++) {
+                if ((ab == 0 && s > R / 4) || (ab == 1 && s < 1)) continue;
+                const unsigned k32 = ab ? keyB[s] : keyA[s];
+                unsigned long long key = ~0ull;
+                if (k32 != 0xFFFFFFFFu) {
+                    const unsigned rank = k32 & 127u;
+                    const int dy = (rank & 1) ? -(int)((rank + 1) >> 1) : (int)(rank >> 1);
+                    const int mx = e + 2 * R - 8 * s + 8 * ab, dx = mx - R;
+                    key = ((unsigned long long)(k32 >> 7) << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
+                          ((unsigned long long)(dy + R) << 12) | (unsigned long long)mx;
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other < key ? other : key;
+                }
+                if (e == 0 && key != ~0ull) atomicMin(&sBest[2 * g + s], key);
+            }
+        }
+        __syncthreads();
+        if (tid < NBLK) {
+            const int i = iBase + tid;
+            const size_t b = bRow + i;
+            if (i >= 0 && i < bw && b >= blk0 && b < blk1 && sBest[tid] != ~0ull) atomicMin(&keys[b - blk0], sBest[tid]);
+        }
+    }
+}
+
+__global__ void search_keys_decode_kernel(const unsigned long long* __restrict__ keys, int32_t* __restrict__ best, size_t n, int R)
+{
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const unsigned long long k = keys[b];
+    best[3 * b + 0] = (int32_t)(k >> 40);
+    best[3 * b + 1] = (int)(k & 0xFFF) - R;
+    best[3 * b + 2] = (int)((k >> 12) & 0xFFF) - R;
+}
+
+template <int R>
+static cudaError_t launch_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
+                             uint32_t* cost, int32_t* best, cudaStream_t st)
+{
+    const int bw = w / 8;
+    const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
+    const int nPos = 8 * (bw - 1) + 2 * R + 1;
+    const dim3 grid((nPos + S3_TILE - 1) / S3_TILE, y1 - y0 + 1);
+    const size_t nb = blk1 - blk0;
+    unsigned long long* keys = nullptr;
+    cudaError_t e;
+    if (best) {
+        if ((e = cudaMallocAsync((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(keys, 0xFF, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+    }
+    satd8x8_search_v3_kernel<R><<<grid, S3_WARPS * 32, 0, st>>>(cur, refPad, strd, w, y0, blk0, blk1, cost, keys);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (best) {
+        search_keys_decode_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(keys, best, nb, R);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaFreeAsync(keys, st)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                     size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
+{
+    (void)h;
+    if (range == 32) return launch_v3<32>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (range == 16) return launch_v3<16>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (range == 8) return launch_v3<8>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    return cudaErrorInvalidValue;
+}
+
+} // namespace x266
