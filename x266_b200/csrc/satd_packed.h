@@ -114,6 +114,17 @@ S3_HD void horizontal8(uint32_t T[32])
     for (int j = 0; j < 4; j++) had8p<2048, 4096, 8192, 1>(&T[8 * j]);
 }
 
+// acc + sum of max(T[j], c_j) over four packed words.  FORM 0: two levels of packed adds, one IDP.2A; FORM 1: one IDP.2A
+// per word (no packed adds: the integer ALU pipe only sees the VIMNMX); FORM 2: one packed add, two IDP.2A.
+template <int FORM>
+S3_HD uint32_t maxsum4(const uint32_t* T, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t acc)
+{
+    const uint32_t m0 = vmax2(T[0], c0), m1 = vmax2(T[1], c1), m2 = vmax2(T[2], c2), m3 = vmax2(T[3], c3);
+    if (FORM == 0) return fold2((m0 + m1) + (m2 + m3), acc);
+    if (FORM == 1) return fold2(m3, fold2(m2, fold2(m1, fold2(m0, acc))));
+    return fold2(m2 + m3, fold2(m0 + m1, acc));
+}
+
 // sum_k max(T[k], C[k]) over the 64 packed coefficients
 S3_HD uint32_t maxsum(const uint32_t T[32], const uint32_t C[32])
 {
