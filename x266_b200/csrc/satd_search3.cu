@@ -12,11 +12,12 @@
 //     from shared memory serves two candidates: 64 B of shared-memory traffic per candidate instead of 256;
 //   * |a-b| = 2 max(a,b) - a - b with sum_k T[k] = 64 x[0][0]: per pair of coefficients one VIMNMX.S16x2, a
 //     quarter of an add and an eighth of an IDP.2A, instead of two VABSDIFF.
-// Work decomposition: a unit is (row of 8x8 blocks, tile of 64 horizontal window positions, fifth of the 2R+1 vertical
-// offsets); ONE WARP = one CTA owns a unit: the window rows it touches (13+7 rows x 72 bytes at R=32) and the T(cur) of
-// the R/4+8 blocks it can serve live in its 4.4 KB of shared memory, 16 such CTAs are resident per SM, and nothing in
+// Work decomposition: a unit is (row of 8x8 blocks, tile of 64 horizontal window positions, third of the 2R+1 vertical
+// offsets); ONE WARP = one CTA owns a unit: the window rows it touches (22+7 rows x 72 bytes at R=32) and the T(cur) of
+// the R/4+8 blocks it can serve live in its 6.6 KB of shared memory, 16 such CTAs are resident per SM, and nothing in
 // the kernel waits on a CTA barrier (a first version with one five-warp CTA per tile spent 24 % of its warp time in
-// the prologue, the epilogue and its barrier; 20 925 small CTAs also leave a last wave that is 98 % full, not 77 %).
+// the prologue, the epilogue and its barrier).  Measured on 1080p +-32: 1/2/3/4/5/7 CTAs per (tile, row) = 0.613 /
+// 0.575 / 0.577 / 0.63 / 0.606 / 0.66 ms -- fewer, longer CTAs amortise the prologue, more of them fill the last wave.
 // Lane (g, e) = (lane>>3, lane&7) owns positions P0+16g+e and P0+16g+8+e; with q = P0/8+2g the blocks of "slot" s are
 // i = q-R/4+s for both positions (mx = e+2R-8s and e+2R+8-8s), so the eight lanes of a group read the same T(cur) and
 // write 32 contiguous bytes of the cost surface.  Tiles follow window positions, not blocks, so no lane is wasted on
@@ -35,9 +36,9 @@ constexpr int S3_TILE = 64;                  // window positions per unit
 constexpr int S3_WP = 72;                    // window pitch in bytes: 64 positions + 7 halo columns (+1)
 constexpr int S3_TCS = 36;                   // T(cur) row: 32 words + 64*cur[0][0] + pad (16-byte rows, distinct banks for 4 blocks)
 constexpr int S3_CTAS_PER_SM = 16;
-constexpr int S3_CHUNKS = 5;                 // CTAs per unit: the 2R+1 vertical offsets are split five ways (65 = 5 x 13)
+template <int R> constexpr int s3_chunks() { return R >= 32 ? 3 : R >= 16 ? 2 : 1; }   // CTAs per (tile, row): ~22 vertical offsets each
 
-template <int R, int ACCF>
+template <int R, int ACCF, int NCH>
 __global__ void __launch_bounds__(32, S3_CTAS_PER_SM)
 satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w, int by0,
                          size_t blk0, size_t blk1, uint32_t* __restrict__ cost, unsigned long long* __restrict__ keys)
@@ -46,7 +47,7 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     constexpr int WS = 2 * R + 8;
     constexpr int NSLOT = R / 4 + 2;
     constexpr int NBLK = R / 4 + 8;
-    constexpr int CH = (SIDE + S3_CHUNKS - 1) / S3_CHUNKS;      // vertical offsets per CTA
+    constexpr int CH = (SIDE + NCH - 1) / NCH;      // vertical offsets per CTA
     constexpr int WR = CH + 7;                                   // window rows a chunk touches
     static_assert(WR <= WS, "chunk window");
     __shared__ __align__(16) uint8_t win[WR * S3_WP];
@@ -117,10 +118,20 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
                 win[idx] = (P0 + xx < padW) ? wsrc[(intptr_t)yy * strd + xx] : (uint8_t)0;
             }
         }
-        for (int idx = lane; idx < 8 * 128; idx += 32) {
-            const int r = idx >> 7, x = idx & 127;
-            const int i = iBase + (x >> 3);
-            curw[r][x] = (x < NBLK * 8 && i >= 0 && i < bw) ? cur[(size_t)(by8 * 8 + r) * w + i * 8 + (x & 7)] : (uint8_t)0;
+        if ((((uintptr_t)cur | (uintptr_t)w) & 7) == 0) {        // 8 pixels of a block row per load
+            for (int idx = lane; idx < 8 * 16; idx += 32) {
+                const int r = idx >> 4, x8 = idx & 15;
+                const int i = iBase + x8;
+                uint2 v = make_uint2(0u, 0u);
+                if (x8 < NBLK && i >= 0 && i < bw) v = __ldg(reinterpret_cast<const uint2*>(cur + (size_t)(by8 * 8 + r) * w + i * 8));
+                *reinterpret_cast<uint2*>(&curw[r][8 * x8]) = v;
+            }
+        } else {
+            for (int idx = lane; idx < 8 * 128; idx += 32) {
+                const int r = idx >> 7, x = idx & 127;
+                const int i = iBase + (x >> 3);
+                curw[r][x] = (x < NBLK * 8 && i >= 0 && i < bw) ? cur[(size_t)(by8 * 8 + r) * w + i * 8 + (x & 7)] : (uint8_t)0;
+            }
         }
         __syncwarp();
 #pragma unroll 1
@@ -229,11 +240,11 @@ __global__ void search_keys_decode_kernel(const unsigned long long* __restrict__
 static int g_accForm = 1;
 void set_search_acc_form(int f) { g_accForm = f; }
 
-template <int R, int ACCF>
+template <int R, int ACCF, int NCH = s3_chunks<R>()>
 static cudaError_t launch_v3f(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
                               uint32_t* cost, int32_t* best, cudaStream_t st)
 {
-    auto kern = satd8x8_search_v3_kernel<R, ACCF>;
+    auto kern = satd8x8_search_v3_kernel<R, ACCF, NCH>;
     const int bw = w / 8;
     const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
     const int nPos = 8 * (bw - 1) + 2 * R + 1;
@@ -246,7 +257,7 @@ static cudaError_t launch_v3f(const uint8_t* cur, const uint8_t* refPad, intptr_
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attrSet[dev] = true;
     }
-    const dim3 grid(nTiles, y1 - y0 + 1, S3_CHUNKS);
+    const dim3 grid(nTiles, y1 - y0 + 1, NCH);
     const size_t nb = blk1 - blk0;
     unsigned long long* keys = nullptr;
     if (best) {
