@@ -38,6 +38,35 @@ constexpr int INTRA_STRIP = 112;            // 32 (negative part) + 66 + padding
 // pair per row, 5 aligned words of the reference strip re-aligned with funnel shifts, 2 pixels per multiply-add.
 // Vertical modes store the four words directly (512 contiguous bytes per warp store).  Horizontal modes are
 // P_v^T of the left reference: the rows go through a padded per-warp tile and are read back as columns.
+// 16 pixels of one prediction row from 17 reference bytes starting at byte `sh/8` of p[0], 9 instructions per 4 pixels:
+// the weights are pre-scaled by 8 so that ((32-f)a + f b + 16) >> 5 is the HIGH byte of each 16-bit lane and the final
+// shift-and-mask folds into the byte permute that interleaves the even and odd pixels.  With the aligned bytes a0..a4,
+// E0 = (a0,a2), O = (a1,a3), E1 = (a2,a4) (16-bit lanes):  even pixels = E0*w0 + O*w1,  odd pixels = O*w0 + E1*w1,
+// and E1 is one permute of this word's and the next word's E0.
+__device__ __forceinline__ void intra_row16(const uint32_t* __restrict__ p, int sh, int f, uint32_t (&out)[4])
+{
+    const uint32_t x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
+    uint32_t E[5];
+    const uint32_t A0 = __funnelshift_r(x0, x1, sh), A1 = __funnelshift_r(x1, x2, sh), A2 = __funnelshift_r(x2, x3, sh),
+                   A3 = __funnelshift_r(x3, x4, sh), A4 = x4 >> sh;
+    E[0] = A0 & 0x00FF00FFu; E[1] = A1 & 0x00FF00FFu; E[2] = A2 & 0x00FF00FFu; E[3] = A3 & 0x00FF00FFu; E[4] = A4 & 0x00FF00FFu;
+    const uint32_t A[4] = { A0, A1, A2, A3 };
+    const uint32_t w0 = (uint32_t)(32 - f) * 8u, w1 = (uint32_t)f * 8u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t O = __byte_perm(A[j], 0u, 0x4341);
+        const uint32_t E1 = __byte_perm(E[j], E[j + 1], 0x5432);
+        const uint32_t pe = E[j] * w0 + (O * w1 + 0x00800080u);
+        const uint32_t po = O * w0 + (E1 * w1 + 0x00800080u);
+        out[j] = __byte_perm(pe, po, 0x7351);
+    }
+}
+
+// Angular modes: lane l generates, for it = 0,1, the 16 pixels (row 16*it + (l>>1), columns 16*(l&1)..+15) of the
+// vertical-family prediction P_v (distance = row, position along the main reference = column): one (idx, f) pair per
+// row.  Vertical modes store the four words directly (512 contiguous bytes per warp store).  Horizontal modes are
+// P_v^T of the left reference: the rows go through a padded per-warp tile and come back as 4x4 byte blocks that are
+// transposed in registers (8 PRMT per block).
 __device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ strip32, int ang, int lane, uint32_t (&w)[2][4])
 {
 #pragma unroll
@@ -45,13 +74,7 @@ __device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ 
         const int row = 16 * it + (lane >> 1), half = lane & 1;
         const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
         const int o = 32 + 4 + 16 * half + idx + 1;                 // byte offset of ref[16*half + idx + 1] in the strip
-        const uint32_t* p = strip32 + (o >> 2);
-        const int sh = (o & 3) * 8;
-        const uint32_t x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
-        w[it][0] = intra_row4(__funnelshift_r(x0, x1, sh), __funnelshift_rc(x0, x1, sh + 8), f);
-        w[it][1] = intra_row4(__funnelshift_r(x1, x2, sh), __funnelshift_rc(x1, x2, sh + 8), f);
-        w[it][2] = intra_row4(__funnelshift_r(x2, x3, sh), __funnelshift_rc(x2, x3, sh + 8), f);
-        w[it][3] = intra_row4(__funnelshift_r(x3, x4, sh), __funnelshift_rc(x3, x4, sh + 8), f);
+        intra_row16(strip32 + (o >> 2), (o & 3) * 8, f, w[it]);
     }
 }
 
@@ -118,16 +141,22 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
                     trow[0] = w[it][0]; trow[1] = w[it][1]; trow[2] = w[it][2]; trow[3] = w[it][3];
                 }
                 __syncwarp();
+                // lane <-> output rows r0..r0+3, columns c0..c0+7: two 4x4 byte blocks of P_v^T
+                const int r0 = 4 * (lane >> 2), c0 = 8 * (lane & 3);
+                uint32_t W[8];
 #pragma unroll
-                for (int it = 0; it < 2; it++) {
-                    const int r = 16 * it + (lane >> 1), c0 = 16 * (lane & 1);          // output row r, columns c0..c0+15 = P_v[c][r]
-                    uint32_t o4[4];
+                for (int k = 0; k < 8; k++) W[k] = *reinterpret_cast<const uint32_t*>(&ttile[warp][c0 + k][r0]);
+                uint32_t o8[4][2];
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        o4[k] = ttile[warp][c0 + 4 * k][r] | (ttile[warp][c0 + 4 * k + 1][r] << 8) |
-                                (ttile[warp][c0 + 4 * k + 2][r] << 16) | ((uint32_t)ttile[warp][c0 + 4 * k + 3][r] << 24);
-                    reinterpret_cast<uint4*>(out)[it * 32 + lane] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t t0 = __byte_perm(W[4 * h], W[4 * h + 1], 0x5140), t1 = __byte_perm(W[4 * h + 2], W[4 * h + 3], 0x5140);
+                    const uint32_t t2 = __byte_perm(W[4 * h], W[4 * h + 1], 0x7362), t3 = __byte_perm(W[4 * h + 2], W[4 * h + 3], 0x7362);
+                    o8[0][h] = __byte_perm(t0, t1, 0x5410); o8[1][h] = __byte_perm(t0, t1, 0x7632);
+                    o8[2][h] = __byte_perm(t2, t3, 0x5410); o8[3][h] = __byte_perm(t2, t3, 0x7632);
                 }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(out) + (r0 + i) * 32 + c0) = make_uint2(o8[i][0], o8[i][1]);
             }
         } else if (mode == 1) {
             int s = left[lane] + top[1 + lane];
