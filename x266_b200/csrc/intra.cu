@@ -14,6 +14,9 @@ __constant__ int c_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, 
                                       -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
 // 8192/|angle| rounded, for angle = -2,-5,-9,-13,-17,-21,-26,-32
 __constant__ int c_intraInv[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+// the same per mode (0 where the angle is not negative)
+__constant__ int c_intraInvMode[35] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4096, 1638, 910, 630, 482, 390, 315,
+                                        256, 315, 390, 482, 630, 910, 1638, 4096, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 __device__ __forceinline__ uint32_t intra_row4(uint32_t a, uint32_t b, int f)
 {
@@ -67,17 +70,18 @@ __device__ __forceinline__ void intra_row16(const uint32_t* __restrict__ p, int 
 // row.  Vertical modes store the four words directly (512 contiguous bytes per warp store).  Horizontal modes are
 // P_v^T of the left reference: the rows go through a padded per-warp tile and come back as 4x4 byte blocks that are
 // transposed in registers (8 PRMT per block).
-__device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ strip32, int ang, int lane, uint32_t (&w)[2][4])
+__device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ strip32, int ref0, int ang, int lane, uint32_t (&w)[2][4])
 {
 #pragma unroll
     for (int it = 0; it < 2; it++) {
         const int row = 16 * it + (lane >> 1), half = lane & 1;
         const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
-        const int o = 32 + 4 + 16 * half + idx + 1;                 // byte offset of ref[16*half + idx + 1] in the strip
+        const int o = ref0 + 16 * half + idx + 1;                   // byte offset of ref[16*half + idx + 1] in the strip
         intra_row16(strip32 + (o >> 2), (o & 3) * 8, f, w[it]);
     }
 }
 
+template <bool ALIGNED>
 __global__ void __launch_bounds__(INTRA_WARPS * 32)
 intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ modes, uint8_t* __restrict__ pred, size_t n)
 {
@@ -85,42 +89,82 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
     __shared__ __align__(16) uint8_t raw[INTRA_WARPS][144];      // left[64] | top[65]
     __shared__ __align__(16) uint8_t ttile[INTRA_WARPS][32][36]; // transpose tile for the horizontal modes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* sref = strip[warp] + 32 + 4;                        // sref[i] = ref[i], i in -32..71; sref-32 is word aligned
     uint8_t* sraw = raw[warp];
+    uint32_t* strip32 = reinterpret_cast<uint32_t*>(strip[warp]);
 
     // software pipeline: the 129 reference bytes and the mode of the NEXT prediction are in flight (registers) while
-    // this one is generated -- otherwise every prediction pays a full DRAM latency with nothing to overlap it
+    // this one is generated -- otherwise every prediction pays a full DRAM latency with nothing to overlap it.
+    // The bytes travel as aligned 32-bit words: lane l holds word l of the 33 words that cover [129q - a, 129q + 129),
+    // a = (129 q) & 3; one shuffle and one funnel shift re-align them to raw[4l .. 4l+3].  Everything the loop needs
+    // per prediction is a pointer bump: no 64-bit multiplies, one compare for the "last prediction of the array" case.
     const size_t pstride = (size_t)gridDim.x * INTRA_WARPS;
-    uint8_t nraw[5] = {};
-    int nmode = 1;
-    auto prefetch = [&](size_t q) {
-        const uint8_t* src = refs + q * 129;
-#pragma unroll
-        for (int k = 0; k < 5; k++) { const int i = lane + 32 * k; if (i < 129) nraw[k] = src[i]; }
-        nmode = modes[q];
-    };
     const size_t p0 = (size_t)blockIdx.x * INTRA_WARPS + warp;
-    if (p0 < n) prefetch(p0);
+    if (p0 >= n) return;
+    int todo = (int)((n - p0 + pstride - 1) / pstride);             // predictions of this warp
+    const uint8_t* src = refs + p0 * 129;                           // reference bytes of the prediction in flight
+    const uint8_t* const srcLast = refs + (n - 1) * 129;            // its word 32 would read past the array
+    const size_t srcStep = pstride * 129;
+    const uint8_t* mp = modes + p0;
+    uint8_t* outp = pred + p0 * 1024;
+    uint32_t nw0 = 0, nw1 = 0;
+    int na = 0, nmode = 1;
+    auto prefetch = [&]() {
+        if (ALIGNED) {
+            na = (int)(reinterpret_cast<uintptr_t>(src) & 3);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(src - na);
+            nw0 = __ldg(wp + lane);
+            if (lane == 0) {
+                if (src != srcLast) nw1 = __ldg(wp + 32);
+                else {                                           // bytes 0..na of word 32 only, never past the array
+                    const uint8_t* t = src - na + 128;
+                    nw1 = t[0];
+                    for (int j = 1; j <= na; j++) nw1 |= (uint32_t)t[j] << (8 * j);
+                }
+            }
+        } else {
+            nw0 = src[4 * lane] | (src[4 * lane + 1] << 8) | (src[4 * lane + 2] << 16) | ((uint32_t)src[4 * lane + 3] << 24);
+            if (lane == 0) nw1 = src[128];
+        }
+        nmode = *mp;
+    };
+    prefetch();
 
-    for (size_t p = p0; p < n; p += pstride) {
+    for (; todo > 0; todo--) {
         const int mode = nmode > 34 ? 1 : nmode;                 // host API rejects > 34; keep device reads in range
-#pragma unroll
-        for (int k = 0; k < 5; k++) { const int i = lane + 32 * k; if (i < 129) sraw[i] = nraw[k]; }
-        if (p + pstride < n) prefetch(p + pstride);
-        __syncwarp();
+        uint32_t R, last;                                        // R = raw[4*lane .. 4*lane+3], last = raw[128]
+        {
+            uint32_t up = __shfl_down_sync(0xffffffffu, nw0, 1);
+            const uint32_t w32 = __shfl_sync(0xffffffffu, nw1, 0);
+            if (lane == 31) up = w32;
+            R = __funnelshift_r(nw0, up, 8 * na);
+            last = (w32 >> (8 * na)) & 0xFFu;
+        }
+        reinterpret_cast<uint32_t*>(sraw)[lane] = R;
+        if (lane == 0) sraw[128] = (uint8_t)last;
+        uint32_t* out = reinterpret_cast<uint32_t*>(outp);
+        src += srcStep; mp += pstride; outp += pstride * 1024;
+        if (todo > 1) prefetch();
         const uint8_t* left = sraw;          // left[i] = pixel (-1, i)
         const uint8_t* top = sraw + 64;      // top[0] = corner, top[1+i] = pixel (i, -1)
-        uint32_t* out = reinterpret_cast<uint32_t*>(pred + p * 1024);
         const bool isVer = mode >= 18;
         const int ang = c_intraAngle[mode];
 
         if (mode >= 2) {
-#pragma unroll
-            for (int i = lane; i <= 71; i += 32) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
+            // reference line ref[-32..65] in the strip, ref[0] at byte ref0: vertical modes ref[i] = top[i] = raw[64+i]
+            // (word aligned at 36), horizontal modes ref[0] = corner, ref[1+j] = left[j] = raw[j] (ref[1] word aligned at 36)
+            // -- so the main part is one 32-bit store per lane straight from the registers.
+            const int ref0 = isVer ? 36 : 35;
+            uint8_t* sref = strip[warp] + ref0;
+            if (isVer) {
+                if (lane >= 16) strip32[9 + lane - 16] = R;
+                if (lane == 0) sref[64] = (uint8_t)last;
+            } else {
+                if (lane < 16) strip32[9 + lane] = R;
+                if (lane == 16) sref[0] = (uint8_t)R;
+            }
             if (ang < 0) {
-                int inv = 0;
-#pragma unroll
-                for (int a = 0; a < 8; a++) if (c_intraAngle[11 + a] == ang) inv = c_intraInv[a];
+                __syncwarp();                                     // sraw complete
+                const int inv = c_intraInvMode[mode];
                 const int k = lane + 1;                           // projects ref[-k], k = 1..32
                 if (-k >= ang) {
                     const int s = (k * inv + 128) >> 8;
@@ -129,7 +173,7 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
             }
             __syncwarp();
             uint32_t w[2][4];
-            intra_angular_rows(reinterpret_cast<const uint32_t*>(strip[warp]), ang, lane, w);
+            intra_angular_rows(strip32, ref0, ang, lane, w);
             if (isVer) {
 #pragma unroll
                 for (int it = 0; it < 2; it++)
@@ -159,6 +203,7 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
                     *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(out) + (r0 + i) * 32 + c0) = make_uint2(o8[i][0], o8[i][1]);
             }
         } else if (mode == 1) {
+            __syncwarp();
             int s = left[lane] + top[1 + lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -166,6 +211,7 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
 #pragma unroll
             for (int it = 0; it < 8; it++) out[it * 32 + lane] = dc;
         } else {
+            __syncwarp();
             const int rsub = lane >> 3, c0 = (lane & 7) * 4;
             const int tr = top[33], bl = left[32];
 #pragma unroll
@@ -491,7 +537,9 @@ cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pr
     if (n == 0) return cudaSuccess;
     const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
     const size_t cap = (size_t)sm_count() * 8;
-    intra32_kernel<<<(unsigned)(want < cap ? want : cap), INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n);
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if ((reinterpret_cast<uintptr_t>(refs) & 3) == 0) intra32_kernel<true><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n);
+    else intra32_kernel<false><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n);
     count_launch();
     return cudaGetLastError();
 }
