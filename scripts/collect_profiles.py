@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Turns the scratch outputs of scripts/gpu_final.sh (gpurun_out/) into the tracked evidence under profiles/ (run here, no GPU):
+launch list (csv + share table), per-kernel ncu summary, DRAM traffic of the bench-size DCT32 launch, bench JSON lines, test log."""
+import csv, io, json, os, shutil, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+# 1. launch list of the bench command
+src = os.path.join(G, "launches.csv")
+if os.path.exists(src):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    open(os.path.join(P, f"{tag}_launches_bench.csv"), "w").writelines(lines)
+    rows = list(csv.reader(io.StringIO("".join(lines))))
+    h = rows[0]
+    kn, val = h.index("Kernel Name"), h.index("Metric Value")
+    unit = h.index("Metric Unit")
+    agg = {}
+    for r in rows[1:]:
+        if len(r) <= val:
+            continue
+        v = float(r[val].replace(",", ""))
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[unit], 1e-6)
+        name = r[kn].split("(")[0][:150]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1; a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(P, f"{tag}_launch_list_bench.md"), "w") as f:
+        f.write("# ncu launch list of `python bench.py --steps 5 --warmup 3` (gpu__time_duration.sum, --clock-control none, first 400 launches)\n\n"
+                "Per-launch times are cold-cache and serialised under the profiler: compare shares, not absolutes. `dct32_imma_kernel` launches are the "
+                "warm-up, the timed steps (2 073 600 blocks each) and the chunks of the e2e host-pointer path; `at::` kernels are torch generating the "
+                "synthetic inputs outside any timed region.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+        for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{name}` | {n} | {ms:.3f} | {100 * ms / tot:.1f}% |\n")
+
+# 2. per-kernel summaries
+for rep, out in (("prof_all.ncu-rep", f"{tag}_ncu_summary.md"), ("prof_dct32_benchsize.ncu-rep", f"{tag}_ncu_dct32_benchsize.md")):
+    rp = os.path.join(G, rep)
+    if os.path.exists(rp):
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rp], capture_output=True, text=True).stdout
+        open(os.path.join(P, out), "w").write(txt.replace(G + "/", "gpurun_out/"))
+
+# 3. DRAM traffic of the bench-size DCT32 launch
+rp = os.path.join(G, "prof_dct32_benchsize.ncu-rep")
+if os.path.exists(rp):
+    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    h, u, r = rows[0], rows[1], rows[-1]
+    def val(m):
+        x = float(r[h.index(m)].replace(",", ""))
+        return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[h.index(m)]]
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    json.dump({"kernel": r[h.index("Kernel Name")], "source": "ncu --set full --clock-control none, bench.py workload (64 frames, 2073600 blocks), one launch",
+               "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr, "algorithmic_bytes_per_launch": 2073600 * 4096,
+               "ratio": (rd + wr) / (2073600 * 4096)}, open(os.path.join(P, "dct32_traffic.json"), "w"), indent=1)
+
+# 4. bench lines, test log
+for a, b in (("bench_final.log", f"{tag}_bench_final_n1.json"), ("bench_ref_final.log", f"{tag}_bench_reference_arm_n1.json")):
+    ap = os.path.join(G, a)
+    if os.path.exists(ap):
+        ls = [l for l in open(ap) if l.startswith("{")]
+        if ls:
+            open(os.path.join(P, b), "w").write(ls[-1])
+if os.path.exists(os.path.join(G, "pytest_final.log")):
+    shutil.copy(os.path.join(G, "pytest_final.log"), os.path.join(P, f"{tag}_pytest_gpu_final.log"))
+print("profiles/ refreshed")
