@@ -30,8 +30,9 @@ for v1 in (1, 3, 2, 0):
 print("v1 == v3:", torch.equal(outs[0][0], outs[1][0]), torch.equal(outs[0][1], outs[1][1]),
       " v2 == v3:", torch.equal(outs[0][0], outs[3][0]), torch.equal(outs[0][1], outs[3][1]))
 xb.tune(1, 0)
-# plain SAD full search (N4)
-for with_cost in (True, False):
+# plain SAD full search (N4): tune(7, 1) = first-generation kernel, 0 = position-tile kernel
+for sv1, with_cost in ((1, True), (0, True), (0, False)):
+    xb.tune(7, sv1)
     c = cost.data_ptr() if with_cost else 0
     for _ in range(2):
         xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c, best.data_ptr(), st)
@@ -41,4 +42,7 @@ for with_cost in (True, False):
         xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c, best.data_ptr(), st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print(f"SAD search cost_surface={with_cost}: {ms:.3f} ms/frame  {nb*4225/ms/1e6:.1f} G cand/s", flush=True)
+    print(f"SAD search {('v2','v1')[sv1]} cost_surface={with_cost}: {ms:.3f} ms/frame  {nb*4225/ms/1e6:.1f} G cand/s", flush=True)
+    if with_cost: outs[('sad', sv1)] = (cost.clone(), best.clone())
+print("SAD v1 == v2:", torch.equal(outs[('sad', 0)][0], outs[('sad', 1)][0]), torch.equal(outs[('sad', 0)][1], outs[('sad', 1)][1]))
+xb.tune(7, 0)

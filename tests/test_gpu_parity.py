@@ -375,14 +375,35 @@ def test_sad_region_sizes(x266, orc, n):
     assert x266.sad(np.zeros((n, n), np.uint8), np.full((n, n), 255, np.uint8)) == 255 * n * n
 
 
-@pytest.mark.parametrize("rng_px", [0, 3, 8, 32])
-def test_sad_search(x266, orc, rng_px):
-    cur, refp = make_frames(72, 40, rng_px, seed=7)
+@pytest.mark.parametrize("rng_px", [0, 3, 8, 16, 32])
+@pytest.mark.parametrize("v1", [0, 1])
+def test_sad_search(x266, orc, rng_px, v1):
+    """v1 = 0: position-tile kernel (two reference windows per thread, R in {8,16,32}); v1 = 1: one CTA per block (any R)"""
+    x266.tune(7, v1)
+    try:
+        cur, refp = make_frames(72, 40, rng_px, seed=7)
+        cost, best = x266.xSad8x8Search(cur, refp, rng_px)
+        wc, wb = orc.sad_search(cur, refp, rng_px, 0, 45)
+        assert np.array_equal(cost, wc) and np.array_equal(best, wb)
+        c, b = x266.xSad8x8Search(cur, refp, rng_px, 7, 20)
+        assert np.array_equal(c, wc[7:20]) and np.array_equal(b, wb[7:20])
+        _, b = x266.xSad8x8Search(cur, refp, rng_px, 7, 20, want_cost=False)
+        assert np.array_equal(b, wb[7:20])
+    finally:
+        x266.tune(7, 0)
+
+
+@pytest.mark.parametrize("rng_px", [8, 32])
+def test_sad_search_wide_frame_and_ties(x266, orc, rng_px):
+    """width 200 = three full position tiles + a ragged one; flat frames: every cost ties and the argmin rule decides"""
+    cur, refp = make_frames(200, 24, rng_px, seed=9)
+    wc, wb = orc.sad_search(cur, refp, rng_px, 0, 75)
     cost, best = x266.xSad8x8Search(cur, refp, rng_px)
-    wc, wb = orc.sad_search(cur, refp, rng_px, 0, 45)
     assert np.array_equal(cost, wc) and np.array_equal(best, wb)
-    c, b = x266.xSad8x8Search(cur, refp, rng_px, 7, 20)
-    assert np.array_equal(c, wc[7:20]) and np.array_equal(b, wb[7:20])
+    flat = np.full((24, 200), 200, np.uint8)
+    flatp = np.full((24 + 2 * rng_px, 200 + 2 * rng_px), 10, np.uint8)
+    c, b = x266.xSad8x8Search(flat, flatp, rng_px)
+    assert (b[:, 1] == 0).all() and (b[:, 2] == 0).all() and (c == 64 * 190).all()
 
 
 # ------------------------------------------------------------------ fused intra mode decision ("next" N1)

@@ -95,6 +95,210 @@ sad8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict_
     }
 }
 
+// ---- full search v2 (R in {8,16,32}): the decomposition of the SATD search v3 (satd_search3.cu) without the
+//      transform.  A unit = (row of blocks, tile of 64 window positions, third of the vertical offsets) = one warp = one
+//      CTA.  Lane (g, e) keeps the 8x8 reference windows of positions P0+16g+e and P0+16g+8+e in registers (16 + 16 words,
+//      re-aligned once per vertical offset with funnel shifts) and walks the <= R/4+2 blocks those positions can serve;
+//      the current block (64 B) is read from shared memory once for both positions: 4 LDS.128 + 32 VABSDIFF4.U8.ACC per
+//      two candidates (v1: 24 LDS.32 + 16 SHF + 16 VABSDIFF4 per candidate, LSU bound).  Argmin as in v3: per (slot,
+//      position) running key in registers, 8-lane shuffle fold, 64-bit atomicMin into a stream-ordered scratch buffer. ----
+constexpr int SAD2_TILE = 64;
+constexpr int SAD2_WW = 18;                  // window pitch in words (72 bytes)
+constexpr int SAD2_CS = 20;                  // words per current block in smem: 16 + 4 pad (four blocks of a warp on distinct banks)
+template <int R> __host__ __device__ constexpr int sad2_chunks() { return R >= 32 ? 3 : R >= 16 ? 2 : 1; }
+
+template <int R>
+__global__ void __launch_bounds__(32, 16)
+sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w, int by0,
+                        size_t blk0, size_t blk1, uint32_t* __restrict__ cost, unsigned long long* __restrict__ keys)
+{
+    constexpr int SIDE = 2 * R + 1;
+    constexpr int NSLOT = R / 4 + 2;
+    constexpr int NBLK = R / 4 + 8;
+    constexpr int CH = (SIDE + sad2_chunks<R>() - 1) / sad2_chunks<R>();
+    constexpr int WR = CH + 7;
+    __shared__ __align__(16) uint32_t win[WR * SAD2_WW];
+    __shared__ __align__(16) uint32_t curs[NBLK * SAD2_CS];
+
+    const int lane = threadIdx.x;
+    const int g = lane >> 3, e = lane & 7;
+    const int bw = w >> 3;
+    const int padW = w + 2 * R;
+    const int xa = 16 * g + e;
+    const int by8 = by0 + blockIdx.y;
+    const int P0 = blockIdx.x * SAD2_TILE;
+    const int my0 = blockIdx.z * CH;
+    const int my1 = (my0 + CH) < SIDE ? (my0 + CH) : SIDE;
+    const int iBase = P0 / 8 - R / 4;
+    const int iq = iBase + 2 * g;
+    const size_t bRow = (size_t)by8 * bw;
+    {
+        const int lo = iBase < 0 ? 0 : iBase;
+        const int hi = (iBase + NBLK - 1) < (bw - 1) ? (iBase + NBLK - 1) : (bw - 1);
+        if (my0 >= SIDE || hi < lo || bRow + hi < blk0 || bRow + lo >= blk1) return;
+    }
+    unsigned keyA[NSLOT], keyB[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) keyA[s] = keyB[s] = 0xFFFFFFFFu;
+
+    {   // stage the window rows of this chunk and the current blocks
+        const uint8_t* wsrc = refPad + ((intptr_t)by8 * 8 + my0) * strd + P0;
+        const int rows = my1 - my0 + 7;
+        if ((((uintptr_t)wsrc | (uintptr_t)strd) & 3) == 0 && P0 + 4 * SAD2_WW <= padW) {
+            for (int idx = lane; idx < rows * SAD2_WW; idx += 32) {
+                const int yy = idx / SAD2_WW, xx = idx - yy * SAD2_WW;
+                win[idx] = __ldg(reinterpret_cast<const uint32_t*>(wsrc + (intptr_t)yy * strd) + xx);
+            }
+        } else {
+            uint8_t* wb = reinterpret_cast<uint8_t*>(win);
+            for (int idx = lane; idx < rows * SAD2_WW * 4; idx += 32) {
+                const int yy = idx / (SAD2_WW * 4), xx = idx - yy * (SAD2_WW * 4);
+                wb[idx] = (P0 + xx < padW) ? wsrc[(intptr_t)yy * strd + xx] : (uint8_t)0;
+            }
+        }
+        if ((((uintptr_t)cur | (uintptr_t)w) & 7) == 0) {
+            for (int idx = lane; idx < 8 * NBLK; idx += 32) {
+                const int r = idx / NBLK, t = idx - r * NBLK;
+                const int i = iBase + t;
+                uint2 v = make_uint2(0u, 0u);
+                if (i >= 0 && i < bw) v = __ldg(reinterpret_cast<const uint2*>(cur + (size_t)(by8 * 8 + r) * w + i * 8));
+                *reinterpret_cast<uint2*>(&curs[t * SAD2_CS + 2 * r]) = v;
+            }
+        } else {
+            uint8_t* cb = reinterpret_cast<uint8_t*>(curs);
+            for (int idx = lane; idx < 64 * NBLK; idx += 32) {
+                const int t = idx >> 6, r = (idx >> 3) & 7, c = idx & 7;
+                const int i = iBase + t;
+                cb[t * SAD2_CS * 4 + r * 8 + c] = (i >= 0 && i < bw) ? cur[(size_t)(by8 * 8 + r) * w + i * 8 + c] : (uint8_t)0;
+            }
+        }
+        __syncwarp();
+    }
+
+    const int sh = (xa & 3) * 8;
+    for (int my = my0; my < my1; my++) {
+        uint32_t A[16], B[16];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t* rw = win + (my - my0 + r) * SAD2_WW + (xa >> 2);
+            const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2], x3 = rw[3], x4 = rw[4];
+            A[2 * r] = __funnelshift_r(x0, x1, sh); A[2 * r + 1] = __funnelshift_r(x1, x2, sh);
+            B[2 * r] = __funnelshift_r(x2, x3, sh); B[2 * r + 1] = __funnelshift_r(x3, x4, sh);
+        }
+        const int dy = my - R;
+        const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
+        uint32_t* cbase = cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R;
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) {
+            const int i = iq + s;
+            const size_t b = bRow + i;
+            if (i >= 0 && i < bw && b >= blk0 && b < blk1) {
+                const bool doA = (s <= R / 4) && (s >= 1 || e == 0);
+                const bool doB = (s >= 1) && (s >= 2 || e == 0);
+                const uint4* cp = reinterpret_cast<const uint4*>(&curs[(2 * g + s) * SAD2_CS]);
+                unsigned a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint4 c = cp[k];
+                    if (s <= R / 4) {
+                        a0 = __vsadu4(A[4 * k], c.x) + a0; a1 = __vsadu4(A[4 * k + 1], c.y) + a1;
+                        a0 = __vsadu4(A[4 * k + 2], c.z) + a0; a1 = __vsadu4(A[4 * k + 3], c.w) + a1;
+                    }
+                    if (s >= 1) {
+                        b0 = __vsadu4(B[4 * k], c.x) + b0; b1 = __vsadu4(B[4 * k + 1], c.y) + b1;
+                        b0 = __vsadu4(B[4 * k + 2], c.z) + b0; b1 = __vsadu4(B[4 * k + 3], c.w) + b1;
+                    }
+                }
+                if (doA) {
+                    const unsigned v = a0 + a1;
+                    if (cost) cbase[s * (SIDE * SIDE - 8)] = v;
+                    const unsigned key = (v << 7) | rank;
+                    keyA[s] = key < keyA[s] ? key : keyA[s];
+                }
+                if (doB) {
+                    const unsigned v = b0 + b1;
+                    if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = v;
+                    const unsigned key = (v << 7) | rank;
+                    keyB[s] = key < keyB[s] ? key : keyB[s];
+                }
+            }
+        }
+    }
+
+    if (keys) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) {
+#pragma unroll
+            for (int ab = 0; ab < 2; ab++) {
+                if ((ab == 0 && s > R / 4) || (ab == 1 && s < 1)) continue;
+                const unsigned k32 = ab ? keyB[s] : keyA[s];
+                unsigned long long key = ~0ull;
+                if (k32 != 0xFFFFFFFFu) {
+                    const unsigned rank = k32 & 127u;
+                    const int dy = (rank & 1) ? -(int)((rank + 1) >> 1) : (int)(rank >> 1);
+                    const int mx = e + 2 * R - 8 * s + 8 * ab, dx = mx - R;
+                    key = ((unsigned long long)(k32 >> 7) << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
+                          ((unsigned long long)(dy + R) << 12) | (unsigned long long)mx;
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other < key ? other : key;
+                }
+                if (e == 0 && key != ~0ull) atomicMin(&keys[bRow + (iq + s) - blk0], key);
+            }
+        }
+    }
+}
+
+__global__ void sad_keys_decode_kernel(const unsigned long long* __restrict__ keys, int32_t* __restrict__ best, size_t n, int R)
+{
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const unsigned long long k = keys[b];
+    best[3 * b + 0] = (int32_t)(k >> 40);
+    best[3 * b + 1] = (int)(k & 0xFFF) - R;
+    best[3 * b + 2] = (int)((k >> 12) & 0xFFF) - R;
+}
+
+template <int R>
+static cudaError_t launch_sad_v2(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
+                                 uint32_t* cost, int32_t* best, cudaStream_t st)
+{
+    auto kern = sad8x8_search_v2_kernel<R>;
+    const int bw = w / 8;
+    const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
+    const int nPos = 8 * (bw - 1) + 2 * R + 1;
+    const dim3 grid((nPos + SAD2_TILE - 1) / SAD2_TILE, y1 - y0 + 1, sad2_chunks<R>());
+    static bool attrSet[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e;
+    if (dev < 0 || dev >= 64 || !attrSet[dev]) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attrSet[dev] = true;
+    }
+    const size_t nb = blk1 - blk0;
+    unsigned long long* keys = nullptr;
+    if (best) {
+        if ((e = cudaMallocAsync((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(keys, 0xFF, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+    }
+    kern<<<grid, 32, 0, st>>>(cur, refPad, strd, w, y0, blk0, blk1, cost, keys);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (best) {
+        sad_keys_decode_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(keys, best, nb, R);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaFreeAsync(keys, st)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+static int g_sadSearchV1 = 0;
+void set_sad_search_v1(int on) { g_sadSearchV1 = on; }
+
 cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, unsigned* out, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned), st);
@@ -111,6 +315,11 @@ cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intp
 {
     if (blk1 <= blk0) return cudaSuccess;
     if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
+    if (!g_sadSearchV1) {
+        if (range == 32) return launch_sad_v2<32>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+        if (range == 16) return launch_sad_v2<16>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+        if (range == 8) return launch_sad_v2<8>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    }
     const int ws = 2 * range + 8, wsw = (ws + 3) / 4 + 1;
     const size_t smem = (size_t)ws * wsw * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
