@@ -82,8 +82,10 @@ enum {
     X266_DCT_IMMA  = 2    /* int8 tensor-core (mma.sync m16n8k32) byte-plane dense product   */
 };
 int xGpuSetDctVariant(int variant);
-/* Diagnostic/tuning hook (not part of the reference-facing surface): key 0 selects the IMMA kernel's
- * (warps, stages, CTAs/SM, staging) instantiation used by scripts/tune_dct.py; -1 = shipped default. */
+/* Diagnostic/tuning hook (not part of the reference-facing surface; 0 / -1 = shipped default everywhere):
+ * key 0 IMMA DCT32 instantiation (warps, stages, CTAs/SM, staging; scripts/tune_dct.py) | 1 SATD search kernel (0 v3 packed
+ * transform domain, 1 one CTA per block, 2/3 v2 strips) | 2 SATD batch variant | 3 CUDA-core DCT 8/16 | 4 blocks per chunk of the
+ * host-pointer DCT pipeline | 5 CUDA-core intra decision | 6 accumulate form of the v3 search | 7 first-generation SAD search. */
 int xGpuTune(int key, int value);
 
 /* 2-D forward 32x32 transform of nBlocks contiguous row-major int16 blocks:
