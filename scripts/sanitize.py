@@ -43,6 +43,11 @@ for R, (w, h) in ((3, (40, 24)), (8, (200, 24)), (32, (200, 16))):
         xb.tune(1, v1)
         c, b = xb.xSatd8x8Search(cur, refp, R)
         check(f"search R={R} mode={v1}", np.array_equal(c, wc) and np.array_equal(b, wb))
+    xb.tune(1, 0)
+    for form in (0, 2, 1):                       # accumulate forms of the v3 kernel (1 = shipped)
+        xb.tune(6, form)
+        c, b = xb.xSatd8x8Search(cur, refp, R, 3, 13)
+        check(f"search v3 R={R} form={form} sub-range", np.array_equal(c, wc[3:13]) and np.array_equal(b, wb[3:13]))
 xb.tune(1, 0)
 refs = rng.integers(0, 256, (70, 129)).astype(np.uint8)
 modes = np.tile(np.arange(35, dtype=np.uint8), 2)
@@ -66,8 +71,15 @@ check("transpose32", np.array_equal(xb.xTranspose32x32Batch(tt), tt.transpose(0,
 sa, sb2 = rng.integers(0, 256, (65, 65)).astype(np.uint8), rng.integers(0, 256, (65, 65)).astype(np.uint8)
 check("sad region", xb.sad(sa, sb2) == o.sad(sa, sb2))
 scur = rng.integers(0, 256, (24, 40)).astype(np.uint8); sref = rng.integers(0, 256, (24 + 16, 40 + 16)).astype(np.uint8)
-c, b = xb.xSad8x8Search(scur, sref, 8)
 wc, wb = o.sad_search(scur, sref, 8, 0, 15)
-check("sad search", np.array_equal(c, wc) and np.array_equal(b, wb))
+for v1 in (0, 1):
+    xb.tune(7, v1)
+    c, b = xb.xSad8x8Search(scur, sref, 8)
+    check(f"sad search v1={v1}", np.array_equal(c, wc) and np.array_equal(b, wb))
+xb.tune(7, 0)
+scur = rng.integers(0, 256, (16, 200)).astype(np.uint8); sref = rng.integers(0, 256, (16 + 64, 200 + 64)).astype(np.uint8)
+c, b = xb.xSad8x8Search(scur, sref, 32)
+wc, wb = o.sad_search(scur, sref, 32, 0, 50)
+check("sad search v2 R=32", np.array_equal(c, wc) and np.array_equal(b, wb))
 print("ALL OK" if ok else "SOME FAILED")
 sys.exit(0 if ok else 1)

@@ -77,7 +77,15 @@ __device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ 
         const int row = 16 * it + (lane >> 1), half = lane & 1;
         const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
         const int o = ref0 + 16 * half + idx + 1;                   // byte offset of ref[16*half + idx + 1] in the strip
-        intra_row16(strip32 + (o >> 2), (o & 3) * 8, f, w[it]);
+        if ((ang & 31) == 0) {                                      // modes 2, 10, 18, 26, 34: every fraction is 0, rows are copies
+            const uint32_t* p = strip32 + (o >> 2);
+            const int sh = (o & 3) * 8;
+            const uint32_t x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
+            w[it][0] = __funnelshift_r(x0, x1, sh); w[it][1] = __funnelshift_r(x1, x2, sh);
+            w[it][2] = __funnelshift_r(x2, x3, sh); w[it][3] = __funnelshift_r(x3, x4, sh);
+        } else {
+            intra_row16(strip32 + (o >> 2), (o & 3) * 8, f, w[it]);
+        }
     }
 }
 
