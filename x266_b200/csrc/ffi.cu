@@ -76,6 +76,35 @@ int sm_count()
     return g_smCache[dev];
 }
 
+static cudaMemPool_t g_pool[MAX_DEV] = {};
+static std::mutex g_poolMu;
+
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
+    if (!g_pool[dev]) {
+        std::lock_guard<std::mutex> lk(g_poolMu);
+        if (!g_pool[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t pool;
+            if ((e = cudaMemPoolCreate(&pool, &props)) != cudaSuccess) return e;
+            unsigned long long keep = ~0ull;
+            if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+            g_pool[dev] = pool;
+        }
+    }
+    return cudaMallocFromPoolAsync(p, bytes, g_pool[dev], st);
+}
+
+cudaError_t scratch_free(void* p, cudaStream_t st) { return cudaFreeAsync(p, st); }
+
 static int ctx_get(Ctx** out)
 {
     int dev = 0;
@@ -186,6 +215,14 @@ extern "C" void xGpuFree(void)
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return;
     Ctx& c = g_ctx[dev];
     std::lock_guard<std::mutex> lk(g_initMu);
+    {
+        std::lock_guard<std::mutex> lp(g_poolMu);
+        if (g_pool[dev]) {                       // scratch of the search kernels: caller has synchronised its streams
+            cudaDeviceSynchronize();
+            cudaMemPoolDestroy(g_pool[dev]);
+            g_pool[dev] = nullptr;
+        }
+    }
     if (!c.ready) return;
     for (int i = 0; i < SLOTS; i++) {
         cudaStreamSynchronize(c.st[i]);

@@ -7,6 +7,10 @@
 namespace x266 {
 
 int sm_count();                 // SMs of the current device (cached per device)
+// Stream-ordered scratch memory from a library-owned pool of the current device (release threshold = keep: a
+// synchronisation between two calls must not hand the memory back to the driver and re-allocate it on the next call).
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st);
+cudaError_t scratch_free(void* p, cudaStream_t st);
 void count_launch();            // bumps the library-wide kernel launch counter
 
 cudaError_t launch_dct32_bfly(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);

@@ -261,7 +261,7 @@ static cudaError_t launch_v3f(const uint8_t* cur, const uint8_t* refPad, intptr_
     const size_t nb = blk1 - blk0;
     unsigned long long* keys = nullptr;
     if (best) {
-        if ((e = cudaMallocAsync((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+        if ((e = scratch_alloc((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(keys, 0xFF, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
     }
     kern<<<grid, 32, 0, st>>>(cur, refPad, strd, w, y0, blk0, blk1, cost, keys);
@@ -271,7 +271,7 @@ static cudaError_t launch_v3f(const uint8_t* cur, const uint8_t* refPad, intptr_
         search_keys_decode_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(keys, best, nb, R);
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = cudaFreeAsync(keys, st)) != cudaSuccess) return e;
+        if ((e = scratch_free(keys, st)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
