@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="8K frames resident per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=8, help="frames per e2e step (host buffers)")
+    ap.add_argument("--e2e-frames", type=int, default=32, help="frames per e2e step (host buffers)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of --impl reference")
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames of the bounded cpu_baseline sample")
     ap.add_argument("--variant", default="auto", choices=["auto", "bfly", "imma"])
@@ -254,7 +254,7 @@ def main():
     hout = torch.empty_like(hin, pin_memory=True)
     hin.copy_(src[:e2e_blocks].cpu())
     hin_np, hout_np = hin.numpy(), hout.numpy()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 6))
     for _ in range(2):
         xb.xDct32Batch(hin_np, *SHIFTS, out=hout_np)
     barrier()
@@ -339,6 +339,44 @@ def main():
                               "roofline": {"bound": "integer ALU pipe / shared memory (not HBM; SURVEY 8(d))", "achieved": 551903296 / (ms * 1e-3) / 1e9,
                                            "peak": peak, "unit": "GB/s", "frac": 551903296 / (ms * 1e-3) / 1e9 / peak, "traffic": None}})
         del cur, refp, cost, best
+        # config 2: one 1080p frame of residuals (2040 blocks) -- latency of a single launch
+        ms = timed(lambda: xb.xDct32BatchDev(sp, dp, 2040, SHIFTS[0], SHIFTS[1], st), 200, warm=20)
+        secondary.append({"metric": "dct32_1080p_frame_launch_latency_us", "value": ms * 1e3, "n_gpus": world, "higher_is_better": False,
+                          "config": "config2: 2040 blocks, one launch, back-to-back launches on one stream (launch bound)",
+                          "roofline": {"bound": "launch latency", "achieved": 2040 * 4096 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": 2040 * 4096 / (ms * 1e-3) / 1e9 / peak, "traffic": None}})
+        # config 4: ONE 3840x2176 frame, every 32x32 region split 1x32^2 / 4x16^2 / 16x8^2 / 64x4^2 by a seeded draw,
+        # the four size classes and the +-32 SATD search of the luma sharded over the ranks (strong scaling, no collective)
+        regions = (3840 // 32) * (2176 // 32)
+        zc = np.random.default_rng(268).integers(0, 4, regions)
+        w4, h4 = 3840, 2160
+        nb4 = (w4 // 8) * (h4 // 8)
+        cur4 = torch.randint(0, 256, (h4, w4), device=dev, generator=g, dtype=torch.uint8)
+        ref4 = torch.randint(0, 256, (h4 + 2 * rg, w4 + 2 * rg), device=dev, generator=g, dtype=torch.uint8)
+        b0, b1 = shard_range(nb4, rank, world)
+        best4 = torch.empty((b1 - b0, 3), device=dev, dtype=torch.int32)
+        shards = []
+        for cls, log2n in enumerate((5, 4, 3, 2)):
+            nblk = int((zc == cls).sum()) * (1024 >> (2 * log2n))
+            lo4, hi4 = shard_range(nblk, rank, world)
+            shards.append((log2n, lo4, hi4 - lo4))
+
+        def config4():
+            for log2n, lo4, cnt in shards:
+                off = lo4 << (2 * log2n + 1)                                         # bytes: this rank's slice of the class array
+                if log2n == 5:
+                    xb.xDct32BatchDev(sp + off, dp + off, cnt, 4, 11, st)
+                else:
+                    xb.xDctNBatchDev(log2n, sp + off, dp + off, cnt, log2n - 1, log2n + 6, st)
+            xb.xSatd8x8SearchDev(cur4.data_ptr(), ref4.data_ptr(), w4 + 2 * rg, w4, h4, rg, b0, b1, 0, best4.data_ptr(), st)
+
+        ms = timed(config4, 5)
+        secondary.append({"metric": "config4_4k_frames_per_s", "value": 1e3 / ms, "n_gpus": world, "ms_per_frame": ms, "scaling": "strong",
+                          "config": "config4: one 3840x2176 frame, mixed 4/8/16/32 forward transforms (8160 regions) + +-32 SATD search argmins "
+                                    "(129600 blocks, 547.6 M candidates), every class and the block rows split over the ranks",
+                          "roofline": {"bound": "integer ALU pipe (search dominates)", "achieved": nb4 * 4225 / (ms * 1e-3) / 1e9, "peak": None,
+                                       "unit": "G candidates/s", "frac": None, "traffic": None}})
+        del cur4, ref4, best4
         # config 4 flavour: the small transforms and the inverse on 1 Gi samples per GPU
         ns = 1 << 30
         for log2n, sh in ((4, (3, 10)), (3, (2, 9)), (2, (1, 8))):

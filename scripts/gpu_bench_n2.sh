@@ -11,5 +11,5 @@ for f in ("gpurun_out/bench_full_n2.log",):
     except Exception as e:
         print(f, 'FAILED', e); print(open(f.replace('.log','.err')).read()[-1500:]); continue
     print(f, {k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['roofline']['frac'], d['e2e']['value'], d['cpu_baseline'])
-    for s in d['secondary']: print("   ", s["metric"], s["value"], s["roofline"]["frac"])
+    for s in d['secondary']: print("   ", s["metric"], f'{s["value"]:.4g}', s["roofline"]["frac"])
 PY

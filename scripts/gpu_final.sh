@@ -10,6 +10,6 @@ python - <<'PY'
 import json
 d=json.loads([l for l in open('gpurun_out/bench_final.log') if l.startswith('{')][-1])
 print({k:d[k] for k in ('value','n_gpus','steps','ms_per_step','gpu_launches','clocks')}); print(d['roofline']); print(d['e2e']); print(d['cpu_baseline'])
-for s in d['secondary']: print(s['metric'], f"{s['value']:.4g}", round(s['roofline']['frac'],3))
+for s in d['secondary']: print(s['metric'], f"{s['value']:.4g}", s['roofline']['frac'] and round(s['roofline']['frac'],3))
 PY
 bash scripts/gpu_profile.sh > gpurun_out/profile_final.log 2>&1; tail -3 gpurun_out/profile_final.log

@@ -41,7 +41,9 @@ constexpr G8 make_g8()
         for (int n = 0; n < 32; n++) g.v[k][n] = (int8_t)g32(k, n);
     return g;
 }
-__constant__ G8 c_g8 = make_g8();
+// global (not __constant__) memory: every lane gathers different bytes of the table for its MMA fragments, which the constant
+// cache serialises 32 ways (measured: 20 us of prologue per launch); plain cached loads take about 2 us.
+__device__ const G8 c_g8 = make_g8();
 
 
 __device__ __forceinline__ int perm_sigma(int mu)  { return 8 * ((mu >> 1) & 3) + 2 * (mu >> 3) + (mu & 1); }
