@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="8K frames resident per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=32, help="frames per e2e step (host buffers)")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step (host buffers); 0 = 32 at N=1, 8 per rank at N>1")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of --impl reference")
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames of the bounded cpu_baseline sample")
     ap.add_argument("--variant", default="auto", choices=["auto", "bfly", "imma"])
@@ -249,6 +249,8 @@ def main():
     value = world * n_blocks * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: the host-pointer C-ABI call, pinned host buffers, copies inside the timed region
+    if args.e2e_frames <= 0:
+        args.e2e_frames = 32 if world == 1 else 8       # pinned host memory: 2 x 2.1 GB at N=1, 2 x 0.53 GB per rank otherwise
     e2e_blocks = args.e2e_frames * BLOCKS_PER_FRAME
     hin = torch.empty((e2e_blocks, 32, 32), dtype=torch.int16, pin_memory=True)
     hout = torch.empty_like(hin, pin_memory=True)
