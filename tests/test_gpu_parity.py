@@ -326,6 +326,49 @@ def test_device_pointer_entry_points(x266, orc):
     assert launches > 0
 
 
+@pytest.mark.parametrize("rng_px", [8, 32])
+def test_search_and_intra_misaligned_device_pointers(x266, orc, rng_px):
+    """The search prologues use 32/64-bit loads when the planes allow it and byte loads otherwise; the intra kernel
+    reads its 129-byte reference records as aligned words when the array is 4-byte aligned.  Odd base addresses and an
+    odd reference stride must take the fallbacks and give the same answers."""
+    import torch
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    w, h = 136, 24
+    cur, refp = make_frames(w, h, rng_px, seed=21)
+    nb = (w // 8) * (h // 8)
+    side = 2 * rng_px + 1
+    strd = refp.shape[1] + 3                                   # odd stride
+    refw = np.zeros((refp.shape[0], strd), np.uint8)
+    refw[:, :refp.shape[1]] = refp
+    dcur = torch.zeros(cur.size + 1, dtype=torch.uint8, device=dev)
+    dref = torch.zeros(refw.size + 1, dtype=torch.uint8, device=dev)
+    dcur[1:] = torch.from_numpy(cur.ravel()).to(dev)            # base address + 1
+    dref[1:] = torch.from_numpy(refw.ravel()).to(dev)
+    cost = torch.empty((nb, side, side), dtype=torch.int32, device=dev)
+    best = torch.empty((nb, 3), dtype=torch.int32, device=dev)
+    for fn, oracle in ((x266.xSatd8x8SearchDev, orc.satd_search), (x266.xSad8x8SearchDev, orc.sad_search)):
+        cost.zero_(); best.zero_()
+        fn(dcur.data_ptr() + 1, dref.data_ptr() + 1, strd, w, h, rng_px, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+        torch.cuda.synchronize()
+        wc, wb = oracle(cur, refp, rng_px, 0, nb)
+        assert np.array_equal(cost.cpu().numpy().astype(np.uint32), wc) and np.array_equal(best.cpu().numpy(), wb)
+    r = np.random.default_rng(3)
+    n = 71
+    refs = r.integers(0, 256, (n, 129)).astype(np.uint8)
+    modes = (np.arange(n) % 35).astype(np.uint8)
+    drefs = torch.zeros(n * 129 + 3, dtype=torch.uint8, device=dev)
+    pred = torch.empty((n, 32, 32), dtype=torch.uint8, device=dev)
+    dmodes = torch.from_numpy(modes).to(dev)
+    for off in (0, 1, 2, 3):                                    # off = 0 is the aligned word path (array ends mid-word)
+        drefs[off:off + n * 129] = torch.from_numpy(refs.ravel()).to(dev)
+        x266.xIntra32PredDev(drefs.data_ptr() + off, dmodes.data_ptr(), pred.data_ptr(), n, st)
+        torch.cuda.synchronize()
+        got = pred.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got[i], orc.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))), (off, i)
+
+
 # ------------------------------------------------------------------------- tiled frames ("next" N2)
 @pytest.mark.parametrize("w,h", [(32, 32), (96, 64), (1920, 1088)])
 def test_frame_residual_dct32(x266, orc, w, h):
