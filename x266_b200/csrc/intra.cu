@@ -65,6 +65,19 @@ __device__ __forceinline__ void intra_row16(const uint32_t* __restrict__ p, int 
     }
 }
 
+// the same for 8 pixels (9 reference bytes): used by the mode-decision kernel, whose A fragments are 8-pixel row pieces
+__device__ __forceinline__ void intra_row8(const uint32_t* __restrict__ p, int sh, int f, uint32_t& out0, uint32_t& out1)
+{
+    const uint32_t x0 = p[0], x1 = p[1], x2 = p[2];
+    const uint32_t A0 = __funnelshift_r(x0, x1, sh), A1 = __funnelshift_r(x1, x2, sh), A2 = x2 >> sh;
+    const uint32_t E0 = A0 & 0x00FF00FFu, E1 = A1 & 0x00FF00FFu, E2 = A2 & 0x00FF00FFu;
+    const uint32_t w0 = (uint32_t)(32 - f) * 8u, w1 = (uint32_t)f * 8u;
+    const uint32_t O0 = __byte_perm(A0, 0u, 0x4341), O1 = __byte_perm(A1, 0u, 0x4341);
+    const uint32_t S0 = __byte_perm(E0, E1, 0x5432), S1 = __byte_perm(E1, E2, 0x5432);
+    out0 = __byte_perm(E0 * w0 + (O0 * w1 + 0x00800080u), O0 * w0 + (S0 * w1 + 0x00800080u), 0x7351);
+    out1 = __byte_perm(E1 * w0 + (O1 * w1 + 0x00800080u), O1 * w0 + (S1 * w1 + 0x00800080u), 0x7351);
+}
+
 // Angular modes: lane l generates, for it = 0,1, the 16 pixels (row 16*it + (l>>1), columns 16*(l&1)..+15) of the
 // vertical-family prediction P_v (distance = row, position along the main reference = column): one (idx, f) pair per
 // row.  Vertical modes store the four words directly (512 contiguous bytes per warp store).  Horizontal modes are
@@ -460,12 +473,7 @@ intra32_decide_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
                         const int row = (sel ? syB : syA) + 4 * s + q;             // distance from the main reference
                         const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
                         const int o = 32 + 4 + sx + idx + 1;                        // byte offset of ref[sx+idx+1] in the strip
-                        const uint32_t w0 = strip32[o >> 2], w1 = strip32[(o >> 2) + 1], w2 = strip32[(o >> 2) + 2];
-                        const int sh = (o & 3) * 8;
-                        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
-                        const uint32_t b0 = __funnelshift_rc(w0, w1, sh + 8), b1 = __funnelshift_rc(w1, w2, sh + 8);
-                        A[s][sel] = intra_row4(a0, b0, f);
-                        A[s][2 + sel] = intra_row4(a1, b1, f);
+                        intra_row8(strip32 + (o >> 2), (o & 3) * 8, f, A[s][sel], A[s][2 + sel]);
                     }
             } else if (mode == 1) {
                 int sum = left[lane] + top[1 + lane];
