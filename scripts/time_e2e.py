@@ -5,11 +5,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import x266_b200 as xb
 torch.cuda.set_device(0)
-n = 8 * 32400
+n = (int(sys.argv[1]) if len(sys.argv) > 1 else 8) * 32400
 hin = torch.randint(-1023, 1024, (n, 32, 32), dtype=torch.int16).pin_memory()
 hout = torch.empty_like(hin).pin_memory()
 a, b = hin.numpy(), hout.numpy()
-for chunk in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+for chunk in ((8192, 16384, 32768, 65536, 131072) if len(sys.argv) > 1 else (1024, 2048, 4096, 8192, 16384, 32768, 65536)):
     xb.tune(4, chunk)
     for _ in range(2):
         xb.xDct32Batch(a, 6, 11, out=b)
@@ -18,7 +18,7 @@ for chunk in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
         xb.xDct32Batch(a, 6, 11, out=b)
     dt = (time.perf_counter() - t) / 5
     print(f"chunk {chunk:6d} blocks: {n / dt / 1e6:6.2f} M blocks/s  ({n * 2048 / dt / 1e9:5.1f} GB/s each way)", flush=True)
-xb.tune(4, 16384)
+xb.tune(4, 0)
 # pure copies for reference
 d = torch.empty((n, 32, 32), dtype=torch.int16, device="cuda")
 torch.cuda.synchronize(); t = time.perf_counter()

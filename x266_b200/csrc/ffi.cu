@@ -26,7 +26,7 @@ namespace x266 {
 // ------------------------------------------------------------------------------------------------
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_dctVariant{X266_DCT_AUTO};
-static std::atomic<size_t> g_dctChunk{16384};      // blocks per pipeline chunk of the host-pointer DCT path (xGpuTune key 4)
+static std::atomic<size_t> g_dctChunk{0};          // blocks per pipeline chunk of the host-pointer DCT path (xGpuTune key 4); 0 = by batch size
 static thread_local char t_err[512] = "";
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -256,7 +256,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 5) { set_decide_v1(value); return 0; }
     if (key == 6) { set_search_acc_form(value); return 0; }
     if (key == 7) { set_sad_search_v1(value); return 0; }
-    if (key == 4 && value > 0) { g_dctChunk.store((size_t)value); return 0; }
+    if (key == 4 && value >= 0) { g_dctChunk.store((size_t)value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }
 
@@ -274,7 +274,12 @@ extern "C" int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int
     if (nBlocks == 0) return 0;
     Ctx* c;
     if (ctx_get(&c)) return -1;
-    return run_chunked(*c, src, 2048, dst, 2048, nBlocks, g_dctChunk.load(),
+    // 32 MiB chunks amortise the per-chunk hand-over best (47.0 GB/s each way of the 48.2 the link gives with both directions busy);
+    // below ~24 chunks the fill and drain of the three-stage pipeline cost more than that, so smaller batches use 16 Ki blocks
+    // (profiles/r01_e2e_chunk_sweep.log).
+    size_t chunk = g_dctChunk.load();
+    if (chunk == 0) chunk = nBlocks >= ((size_t)3 << 18) ? 32768 : 16384;
+    return run_chunked(*c, src, 2048, dst, 2048, nBlocks, chunk,
                        [&](void* di, void* dO, size_t n, cudaStream_t st) {
                            return dct32_dispatch((const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
                        });
