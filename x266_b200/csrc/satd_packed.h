@@ -1,6 +1,6 @@
 // satd_packed.h -- packed 16-bit, biased 2-D Hadamard of 8-bit pixel blocks and the max-sum cost form used by
 // the full-search kernel v3 (satd_search3.cu).  Host+device: the same inline functions are compiled by g++ in
-// tests/c/satd_packed_model.cpp, so the arithmetic is checked on the CPU against the oracle without a GPU.
+// tests/c/satd_packed_model.cpp, so the arithmetic is checked on the CPU against satd8x8 of the difference without a GPU.
 //
 // What is computed (src_tb/satd.c:31-118 applied to diff = cur - ref(mv)):  the Hadamard transform is linear, so
 // T(diff) = T(cur) - T(ref) and the cost is (sum_k |Tcur[k] - Tref[k]| + 2) >> 2 -- exact because a transform of
