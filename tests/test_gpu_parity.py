@@ -1,6 +1,7 @@
 """GPU suite: bit-exact parity of the CUDA path, called through the C ABI, against the oracle, the
 committed reference vectors, the KAT hashes, and (when oracle/_ref travelled) the reference itself."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -272,6 +273,22 @@ def test_satd_search_extreme_patterns(x266, orc, rng_px):
         cost, best = x266.xSatd8x8Search(c, f, rng_px)
         wc, wb = orc.satd_search(c, f, rng_px, 0, (w // 8) * (h // 8))
         assert np.array_equal(cost, wc) and np.array_equal(best, wb)
+
+
+def test_satd_search_config3_golden(x266):
+    """Config 3 at full size against the committed known-answer file minted from the unmodified reference (no CPU checker
+    involved at test time): all 32400 argmins, and the full cost surfaces of the sampled blocks by FNV-1a-64."""
+    from search_frames import config3_frames, fnv1a64
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "search_kat.npz"))
+    cur, refp = config3_frames()
+    _, best = x266.xSatd8x8Search(cur, refp, 32, want_cost=False)
+    assert np.array_equal(best, g["best"])
+    interior = [by * 240 + bx for by in range(8, 127, 17) for bx in range(8, 232, 23)]
+    assert all(best[b, 1] == 5 and best[b, 2] == -3 for b in interior)
+    for k in range(0, len(g["sample"]), 4):
+        b = int(g["sample"][k])
+        cost, bb = x266.xSatd8x8Search(cur, refp, 32, b, b + 1)
+        assert fnv1a64(cost[0]) == int(g["sample_fnv"][k]) and np.array_equal(bb[0], g["best"][b])
 
 
 def test_satd_search_1080p_sample(x266, orc):

@@ -245,3 +245,18 @@ def test_packed_search_arithmetic_model(orc, tmp_path):
     want = orc.satd((cur.astype(np.int16) - ref.astype(np.int16)).reshape(-1))
     assert np.array_equal(cost, want)
     assert worst.value == 16352
+
+
+def test_search_golden_pins_oracle_search(orc):
+    """tests/golden/search_kat.npz was minted from the unmodified reference satd8x8 on config 3 (splitmix64
+    planes, global motion (+5,-3), +-32).  The oracle's search loop must reproduce its argmins and cost surfaces on a few of
+    the sampled blocks, and the committed generator must still produce the same planes."""
+    from search_frames import config3_frames, fnv1a64
+    g = np.load(os.path.join(GOLDEN, "search_kat.npz"))
+    cur, refp = config3_frames()
+    assert fnv1a64(cur[:64]) != 0 and int(g["fnv_cur"]) == fnv1a64(cur)
+    for k in (0, 57, 131, 255 % len(g["sample"])):
+        b = int(g["sample"][k])
+        cost, best = orc.satd_search(cur, refp, 32, b, b + 1)
+        assert np.array_equal(best[0], g["best"][b])
+        assert fnv1a64(cost[0]) == int(g["sample_fnv"][k])
