@@ -116,26 +116,22 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
     // software pipeline: the 129 reference bytes and the mode of the NEXT prediction are in flight (registers) while
     // this one is generated -- otherwise every prediction pays a full DRAM latency with nothing to overlap it.
     // The bytes travel as aligned 32-bit words: lane l holds word l of the 33 words that cover [129q - a, 129q + 129),
-    // a = (129 q) & 3; one shuffle and one funnel shift re-align them to raw[4l .. 4l+3].  Everything the loop needs
-    // per prediction is a pointer bump: no 64-bit multiplies, one compare for the "last prediction of the array" case.
-    const size_t pstride = (size_t)gridDim.x * INTRA_WARPS;
-    const size_t p0 = (size_t)blockIdx.x * INTRA_WARPS + warp;
-    if (p0 >= n) return;
-    int todo = (int)((n - p0 + pstride - 1) / pstride);             // predictions of this warp
-    const uint8_t* src = refs + p0 * 129;                           // reference bytes of the prediction in flight
-    const uint8_t* const srcLast = refs + (n - 1) * 129;            // its word 32 would read past the array
-    const size_t srcStep = pstride * 129;
-    const uint8_t* mp = modes + p0;
-    uint8_t* outp = pred + p0 * 1024;
+    // a = (129 q) & 3; one shuffle and one funnel shift re-align them to raw[4l .. 4l+3].  Addresses come from a 32-bit
+    // prediction index with one wide multiply-add each.
+    const uint32_t pstride = gridDim.x * INTRA_WARPS;
+    const uint32_t nLast = (uint32_t)n - 1;                          // n < 2^32: a prediction is 1 KiB of output
+    uint32_t p = blockIdx.x * INTRA_WARPS + warp;                    // prediction being generated
+    if (p > nLast) return;
     uint32_t nw0 = 0, nw1 = 0;
     int na = 0, nmode = 1;
-    auto prefetch = [&]() {
+    auto prefetch = [&](uint32_t q) {
+        const uint8_t* src = refs + (size_t)q * 129;
         if (ALIGNED) {
             na = (int)(reinterpret_cast<uintptr_t>(src) & 3);
             const uint32_t* wp = reinterpret_cast<const uint32_t*>(src - na);
             nw0 = __ldg(wp + lane);
             if (lane == 0) {
-                if (src != srcLast) nw1 = __ldg(wp + 32);
+                if (q != nLast) nw1 = __ldg(wp + 32);
                 else {                                           // bytes 0..na of word 32 only, never past the array
                     const uint8_t* t = src - na + 128;
                     nw1 = t[0];
@@ -146,11 +142,11 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
             nw0 = src[4 * lane] | (src[4 * lane + 1] << 8) | (src[4 * lane + 2] << 16) | ((uint32_t)src[4 * lane + 3] << 24);
             if (lane == 0) nw1 = src[128];
         }
-        nmode = *mp;
+        nmode = modes[q];
     };
-    prefetch();
+    prefetch(p);
 
-    for (; todo > 0; todo--) {
+    for (; p <= nLast; p += pstride) {
         const int mode = nmode > 34 ? 1 : nmode;                 // host API rejects > 34; keep device reads in range
         uint32_t R, last;                                        // R = raw[4*lane .. 4*lane+3], last = raw[128]
         {
@@ -162,9 +158,8 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
         }
         reinterpret_cast<uint32_t*>(sraw)[lane] = R;
         if (lane == 0) sraw[128] = (uint8_t)last;
-        uint32_t* out = reinterpret_cast<uint32_t*>(outp);
-        src += srcStep; mp += pstride; outp += pstride * 1024;
-        if (todo > 1) prefetch();
+        uint32_t* out = reinterpret_cast<uint32_t*>(pred + (size_t)p * 1024);
+        if (p + pstride <= nLast) prefetch(p + pstride);
         const uint8_t* left = sraw;          // left[i] = pixel (-1, i)
         const uint8_t* top = sraw + 64;      // top[0] = corner, top[1+i] = pixel (i, -1)
         const bool isVer = mode >= 18;
@@ -551,6 +546,7 @@ cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint3
 cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    if (n > ((size_t)1 << 31)) return cudaErrorInvalidValue;          // 32-bit prediction index in the kernel (2 TiB of output)
     const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
     const size_t cap = (size_t)sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);

@@ -187,7 +187,7 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
         }
         const int dy = my - R;
         const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
-        uint32_t* cbase = cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R;
+        uint32_t* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) {
             const int i = iq + s;

@@ -191,7 +191,7 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
         const int dy = my - R;
         const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
         // cost index of (slot s, position A) = cbase + s * (SIDE*SIDE - 8); position B: + 8
-        uint32_t* cbase = cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R;
+        uint32_t* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
 
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) {
