@@ -308,13 +308,21 @@ def test_satd_search_1080p_sample(x266, orc):
 
 
 # --------------------------------------------------------------------------------------- intra
-def test_intra32_all_modes(x266, orc):
+@pytest.mark.parametrize("swar", [0, 1])
+def test_intra32_all_modes(x266, orc, swar):
+    """swar = 0: fractional angles on the tensor cores (W x Hankel product, 8 IMMA per prediction), copies / DC / planar on CUDA
+    cores; swar = 1: every angular mode through the CUDA-core SWAR interpolation"""
     r = np.random.default_rng(5)
     refs = r.integers(0, 256, (35 * 6, 129)).astype(np.uint8)
     modes = np.tile(np.arange(35, dtype=np.uint8), 6)
     refs[0:35] = 0
     refs[35:70] = 255
-    pred = x266.xIntra32Pred(refs, modes)
+    refs[70:105] = r.choice([0, 255], (35, 129)).astype(np.uint8)      # extremes: every weighted sum at its limits
+    x266.tune(8, swar)
+    try:
+        pred = x266.xIntra32Pred(refs, modes)
+    finally:
+        x266.tune(8, 0)
     for i in range(modes.size):
         assert np.array_equal(pred[i], orc.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))), int(modes[i])
 

@@ -256,6 +256,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 5) { set_decide_v1(value); return 0; }
     if (key == 6) { set_search_acc_form(value); return 0; }
     if (key == 7) { set_sad_search_v1(value); return 0; }
+    if (key == 8) { set_intra_swar(value); return 0; }
     if (key == 4 && value >= 0) { g_dctChunk.store((size_t)value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }

@@ -8,6 +8,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <mutex>
+#include <vector>
+
 namespace x266 {
 
 __constant__ int c_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
@@ -26,6 +29,79 @@ __device__ __forceinline__ uint32_t intra_row4(uint32_t a, uint32_t b, int f)
     const uint32_t pe = ((ae * (uint32_t)(32 - f) + be * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
     const uint32_t po = ((ao * (uint32_t)(32 - f) + bo * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
     return pe | (po << 8);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core form of the angular modes with a fractional angle (|angle| < 32, modes 3..17 and 19..33).
+// The vertical-family prediction is linear in the reference line:  P[y][x] = sum_k W[y][k] * H[k][x]  with the Hankel
+// matrix H[k][x] = ref[base + k + x] and two weights per row, W[y][idx_y + 1 - base] = 8 (32 - f_y), W[y][.. + 1] = 8 f_y
+// (base = smallest idx_y + 1 of the mode, so k <= 27 < 32: ONE k32 step).  The weights carry the factor 8, so the pixel is
+// byte 1 of the 32-bit sum; the rounding constant 128 rides on tap k = 31, whose Hankel row is patched to ones (one LOP3
+// per register); a row with f = 0 uses weight 255 and rounding 255, which is exact for every 8-bit a: (255 a + 255) >> 8 = a.
+//   vertical modes:   D = W * H      A = W from a per-mode fragment table, B = 4-byte windows of the reference strip
+//   horizontal modes: D = H^T * W^T  A = the same windows of the left reference, B = W^T from the table
+// so horizontal predictions come out in output orientation and nothing is transposed.  8 IMMA.16832.U8.U8 per prediction
+// instead of 512 two-pixel multiply-adds; the accumulators leave through a per-warp tile as byte pairs (one PRMT each) and
+// are stored with the same two 512-byte instructions as before.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_u8u8_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+static const int h_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
+                                      -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+
+// Fragment table, [mode][half][lane] as uint4: vertical modes hold the A fragments of W (half = m16 tile, registers a0..a3),
+// horizontal modes the B fragments of W^T (half 0 = column tiles 0,1, half 1 = tiles 2,3; registers b0, b1 of each).
+// Output columns are permuted over the n8 tiles -- fragment column n of tile t = 2u+h is pixel x = 16u + 4(n>>1) + 2h + (n&1) --
+// so that the accumulators of a tile pair give every lane FOUR adjacent pixels of a row (one 32-bit word).
+static std::vector<uint32_t> intra_mma_table_host()
+{
+    std::vector<uint32_t> tab(35 * 256, 0u);
+    for (int mode = 2; mode < 35; mode++) {
+        const int ang = h_intraAngle[mode];
+        if ((ang & 31) == 0 && ang != 0) continue;                  // |angle| = 32: pure copies, handled without multiplies
+        const int base = ang >= 0 ? (ang >> 5) + 1 : ang + 1;
+        uint8_t W[32][32] = {};
+        for (int y = 0; y < 32; y++) {
+            const int t = (y + 1) * ang, idx = t >> 5, f = t & 31, k = idx + 1 - base;
+            if (f == 0) { W[y][k] = 255; W[y][31] = 255; }
+            else { W[y][k] = (uint8_t)(8 * (32 - f)); W[y][k + 1] = (uint8_t)(8 * f); W[y][31] = 128; }
+        }
+        for (int lane = 0; lane < 32; lane++) {
+            const int g = lane >> 2, q = lane & 3;
+            for (int r8 = 0; r8 < 8; r8++) {
+                int row, k0;
+                if (mode >= 18) { const int m = r8 >> 2, r = r8 & 3; row = 16 * m + g + 8 * (r & 1); k0 = 16 * (r >> 1) + 4 * q; }
+                else { const int t = r8 >> 1, r = r8 & 1; row = 16 * (t >> 1) + 4 * (g >> 1) + 2 * (t & 1) + (g & 1); k0 = 16 * r + 4 * q; }
+                uint32_t v = 0;
+                for (int i = 0; i < 4; i++) v |= (uint32_t)W[row][k0 + i] << (8 * i);
+                tab[mode * 256 + (r8 >> 2) * 128 + lane * 4 + (r8 & 3)] = v;
+            }
+        }
+    }
+    return tab;
+}
+
+static const uint32_t* intra_mma_table_dev(cudaError_t* err)
+{
+    static const uint32_t* dTab[64] = {};
+    static std::mutex mu;
+    int dev = 0;
+    *err = cudaGetDevice(&dev);
+    if (*err != cudaSuccess) return nullptr;
+    if (dev < 0 || dev >= 64) { *err = cudaErrorInvalidDevice; return nullptr; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!dTab[dev]) {
+        const std::vector<uint32_t> h = intra_mma_table_host();
+        uint32_t* d = nullptr;
+        if ((*err = cudaMalloc((void**)&d, h.size() * sizeof(uint32_t))) != cudaSuccess) return nullptr;
+        if ((*err = cudaMemcpy(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return nullptr; }
+        dTab[dev] = d;
+    }
+    return dTab[dev];
 }
 
 // One warp per prediction.  Lane l produces, for it = 0..7, the 4 pixels (row 4*it + (l>>3), columns
@@ -104,11 +180,12 @@ __device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ 
 
 template <bool ALIGNED>
 __global__ void __launch_bounds__(INTRA_WARPS * 32)
-intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ modes, uint8_t* __restrict__ pred, size_t n)
+intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ modes, uint8_t* __restrict__ pred, size_t n,
+               const uint32_t* __restrict__ mmaTab, int useMma)
 {
     __shared__ __align__(16) uint8_t strip[INTRA_WARPS][INTRA_STRIP + 16];
     __shared__ __align__(16) uint8_t raw[INTRA_WARPS][144];      // left[64] | top[65]
-    __shared__ __align__(16) uint8_t ttile[INTRA_WARPS][32][36]; // transpose tile for the horizontal modes
+    __shared__ __align__(16) uint8_t tile[INTRA_WARPS][32 * 48]; // output tile of the tensor-core path (pitch 48) / transpose tile (pitch 36)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* sraw = raw[warp];
     uint32_t* strip32 = reinterpret_cast<uint32_t*>(strip[warp]);
@@ -188,6 +265,78 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
                 }
             }
             __syncwarp();
+            if (useMma && (ang & 31) != 0) {
+                // ---- tensor-core path (see the comment above mma_u8u8_16832)
+                const int g4 = lane >> 2, q4 = lane & 3;
+                const int base = ang >= 0 ? (ang >> 5) + 1 : ang + 1;
+                const uint32_t keep = q4 == 3 ? 0x00FFFFFFu : 0xFFFFFFFFu, one = q4 == 3 ? 0x01000000u : 0u;   // Hankel row k = 31 := 1
+                const uint4* tp = reinterpret_cast<const uint4*>(mmaTab) + mode * 64 + lane;
+                const uint4 T0 = __ldg(tp), T1 = __ldg(tp + 32);
+                uint32_t* t32 = reinterpret_cast<uint32_t*>(tile[warp]);
+                // one output word: pixel = byte 1 of each of the four sums
+                auto word = [](const int (&a)[4], const int (&b)[4], int r) {
+                    return __byte_perm(__byte_perm((uint32_t)a[2 * r], (uint32_t)a[2 * r + 1], 0x5151),
+                                       __byte_perm((uint32_t)b[2 * r], (uint32_t)b[2 * r + 1], 0x5151), 0x5410);
+                };
+                if (isVer) {
+                    // B = Hankel windows with permuted columns: column n = g of tile (u, h) is pixel 16u + 4(g>>1) + 2h + (g&1)
+                    const int cb = ref0 + base + 4 * q4 + 4 * (g4 >> 1) + (g4 & 1);
+                    const uint32_t* wp = strip32 + (cb >> 2);
+                    const int sh = (cb & 3) * 8;
+                    uint32_t w0[3], w2[3];                                   // windows at byte offsets 16j and 16j + 2
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const uint32_t xa = wp[4 * j], xb = wp[4 * j + 1], xc = wp[4 * j + 2];
+                        const uint32_t lo = __funnelshift_r(xa, xb, sh), hi = __funnelshift_r(xb, xc, sh);
+                        w0[j] = lo;
+                        w2[j] = __byte_perm(lo, hi, 0x5432);
+                    }
+                    const uint32_t p0[2] = { (w0[1] & keep) | one, (w0[2] & keep) | one };
+                    const uint32_t p2[2] = { (w2[1] & keep) | one, (w2[2] & keep) | one };
+#pragma unroll
+                    for (int m = 0; m < 2; m++) {
+                        const uint4 A = m ? T1 : T0;
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            int da[4], db[4];
+                            mma_u8u8_16832(da, A.x, A.y, A.z, A.w, w0[u], p0[u]);
+                            mma_u8u8_16832(db, A.x, A.y, A.z, A.w, w2[u], p2[u]);
+                            t32[(16 * m + g4) * 12 + 4 * u + q4] = word(da, db, 0);
+                            t32[(16 * m + g4 + 8) * 12 + 4 * u + q4] = word(da, db, 1);
+                        }
+                    }
+                } else {
+                    // A = Hankel windows of the left reference (rows y = 16m + g, g + 8), B = W^T from the table
+                    const int ca = ref0 + base + 4 * q4 + g4;
+                    const uint32_t* wp = strip32 + (ca >> 2);
+                    const int sh = (ca & 3) * 8;
+                    uint32_t win[6];
+#pragma unroll
+                    for (int j = 0; j < 6; j++) win[j] = __funnelshift_r(wp[2 * j], wp[2 * j + 1], sh);
+                    uint32_t wpat[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) wpat[j] = (win[j + 2] & keep) | one;
+#pragma unroll
+                    for (int m = 0; m < 2; m++) {
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const uint4 B = u ? T1 : T0;
+                            int da[4], db[4];
+                            mma_u8u8_16832(da, win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], B.x, B.y);
+                            mma_u8u8_16832(db, win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], B.z, B.w);
+                            t32[(16 * m + g4) * 12 + 4 * u + q4] = word(da, db, 0);
+                            t32[(16 * m + g4 + 8) * 12 + 4 * u + q4] = word(da, db, 1);
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 2; it++)
+                    reinterpret_cast<uint4*>(out)[it * 32 + lane] =
+                        *reinterpret_cast<const uint4*>(&tile[warp][(16 * it + (lane >> 1)) * 48 + 16 * (lane & 1)]);
+                __syncwarp();
+                continue;
+            }
             uint32_t w[2][4];
             intra_angular_rows(strip32, ref0, ang, lane, w);
             if (isVer) {
@@ -197,7 +346,7 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
             } else {
 #pragma unroll
                 for (int it = 0; it < 2; it++) {
-                    uint32_t* trow = reinterpret_cast<uint32_t*>(&ttile[warp][16 * it + (lane >> 1)][16 * (lane & 1)]);
+                    uint32_t* trow = reinterpret_cast<uint32_t*>(&tile[warp][(16 * it + (lane >> 1)) * 36 + 16 * (lane & 1)]);
                     trow[0] = w[it][0]; trow[1] = w[it][1]; trow[2] = w[it][2]; trow[3] = w[it][3];
                 }
                 __syncwarp();
@@ -205,7 +354,7 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
                 const int r0 = 4 * (lane >> 2), c0 = 8 * (lane & 3);
                 uint32_t W[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) W[k] = *reinterpret_cast<const uint32_t*>(&ttile[warp][c0 + k][r0]);
+                for (int k = 0; k < 8; k++) W[k] = *reinterpret_cast<const uint32_t*>(&tile[warp][(c0 + k) * 36 + r0]);
                 uint32_t o8[4][2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -543,6 +692,9 @@ cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint3
     return cudaGetLastError();
 }
 
+static int g_intraSwar = 0;      // tuning/diagnostic: 1 = CUDA-core SWAR interpolation for every angular mode
+void set_intra_swar(int on) { g_intraSwar = on; }
+
 cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
@@ -550,8 +702,11 @@ cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pr
     const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
     const size_t cap = (size_t)sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if ((reinterpret_cast<uintptr_t>(refs) & 3) == 0) intra32_kernel<true><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n);
-    else intra32_kernel<false><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n);
+    cudaError_t e;
+    const uint32_t* tab = intra_mma_table_dev(&e);
+    if (!tab) return e;
+    if ((reinterpret_cast<uintptr_t>(refs) & 3) == 0) intra32_kernel<true><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n, tab, !g_intraSwar);
+    else intra32_kernel<false><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n, tab, !g_intraSwar);
     count_launch();
     return cudaGetLastError();
 }
