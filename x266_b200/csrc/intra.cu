@@ -55,8 +55,9 @@ static const int h_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, 
 
 // Fragment table, [mode][half][lane] as uint4: vertical modes hold the A fragments of W (half = m16 tile, registers a0..a3),
 // horizontal modes the B fragments of W^T (half 0 = column tiles 0,1, half 1 = tiles 2,3; registers b0, b1 of each).
-// Output columns are permuted over the n8 tiles -- fragment column n of tile t = 2u+h is pixel x = 16u + 4(n>>1) + 2h + (n&1) --
-// so that the accumulators of a tile pair give every lane FOUR adjacent pixels of a row (one 32-bit word).
+// Output columns are permuted over the n8 tiles -- fragment column n of tile t is pixel x = 8(n>>1) + 2t + (n&1) -- so that the
+// accumulators of the four tiles give lane (g, q) the EIGHT adjacent pixels 8q..8q+7 of rows g and g+8: the prediction is stored
+// straight from the registers, 8 bytes per lane and full 32-byte sectors per row, with no shared-memory round trip.
 static std::vector<uint32_t> intra_mma_table_host()
 {
     std::vector<uint32_t> tab(35 * 256, 0u);
@@ -75,7 +76,7 @@ static std::vector<uint32_t> intra_mma_table_host()
             for (int r8 = 0; r8 < 8; r8++) {
                 int row, k0;
                 if (mode >= 18) { const int m = r8 >> 2, r = r8 & 3; row = 16 * m + g + 8 * (r & 1); k0 = 16 * (r >> 1) + 4 * q; }
-                else { const int t = r8 >> 1, r = r8 & 1; row = 16 * (t >> 1) + 4 * (g >> 1) + 2 * (t & 1) + (g & 1); k0 = 16 * r + 4 * q; }
+                else { const int t = r8 >> 1, r = r8 & 1; row = 8 * (g >> 1) + 2 * t + (g & 1); k0 = 16 * r + 4 * q; }
                 uint32_t v = 0;
                 for (int i = 0; i < 4; i++) v |= (uint32_t)W[row][k0 + i] << (8 * i);
                 tab[mode * 256 + (r8 >> 2) * 128 + lane * 4 + (r8 & 3)] = v;
@@ -233,8 +234,10 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
             R = __funnelshift_r(nw0, up, 8 * na);
             last = (w32 >> (8 * na)) & 0xFFu;
         }
-        reinterpret_cast<uint32_t*>(sraw)[lane] = R;
-        if (lane == 0) sraw[128] = (uint8_t)last;
+        if (mode < 2 || (mode >= 11 && mode <= 25)) {          // only DC / planar and the negative-angle projections read the staged bytes
+            reinterpret_cast<uint32_t*>(sraw)[lane] = R;
+            if (lane == 0) sraw[128] = (uint8_t)last;
+        }
         uint32_t* out = reinterpret_cast<uint32_t*>(pred + (size_t)p * 1024);
         if (p + pstride <= nLast) prefetch(p + pstride);
         const uint8_t* left = sraw;          // left[i] = pixel (-1, i)
@@ -272,38 +275,35 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
                 const uint32_t keep = q4 == 3 ? 0x00FFFFFFu : 0xFFFFFFFFu, one = q4 == 3 ? 0x01000000u : 0u;   // Hankel row k = 31 := 1
                 const uint4* tp = reinterpret_cast<const uint4*>(mmaTab) + mode * 64 + lane;
                 const uint4 T0 = __ldg(tp), T1 = __ldg(tp + 32);
-                uint32_t* t32 = reinterpret_cast<uint32_t*>(tile[warp]);
-                // one output word: pixel = byte 1 of each of the four sums
+                uint8_t* orow = reinterpret_cast<uint8_t*>(out) + g4 * 32 + 8 * q4;      // row g, pixels 8q..8q+7
+                // pixel = byte 1 of each sum: four sums -> one word
                 auto word = [](const int (&a)[4], const int (&b)[4], int r) {
                     return __byte_perm(__byte_perm((uint32_t)a[2 * r], (uint32_t)a[2 * r + 1], 0x5151),
                                        __byte_perm((uint32_t)b[2 * r], (uint32_t)b[2 * r + 1], 0x5151), 0x5410);
                 };
                 if (isVer) {
-                    // B = Hankel windows with permuted columns: column n = g of tile (u, h) is pixel 16u + 4(g>>1) + 2h + (g&1)
-                    const int cb = ref0 + base + 4 * q4 + 4 * (g4 >> 1) + (g4 & 1);
+                    // B = Hankel windows with permuted columns: column n = g of tile t is pixel 8(g>>1) + 2t + (g&1)
+                    const int cb = ref0 + base + 4 * q4 + 8 * (g4 >> 1) + (g4 & 1);
                     const uint32_t* wp = strip32 + (cb >> 2);
                     const int sh = (cb & 3) * 8;
-                    uint32_t w0[3], w2[3];                                   // windows at byte offsets 16j and 16j + 2
+                    uint32_t wl[4], wh[4];                                   // windows at byte offsets 2t and 16 + 2t
 #pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        const uint32_t xa = wp[4 * j], xb = wp[4 * j + 1], xc = wp[4 * j + 2];
-                        const uint32_t lo = __funnelshift_r(xa, xb, sh), hi = __funnelshift_r(xb, xc, sh);
-                        w0[j] = lo;
-                        w2[j] = __byte_perm(lo, hi, 0x5432);
+                    for (int j = 0; j < 2; j++) {
+                        const uint32_t xa = wp[4 * j], xb = wp[4 * j + 1], xc = wp[4 * j + 2], xd = wp[4 * j + 3];
+                        const uint32_t lo = __funnelshift_r(xa, xb, sh), mid = __funnelshift_r(xb, xc, sh), hi = __funnelshift_r(xc, xd, sh);
+                        uint32_t* w = j ? wh : wl;
+                        w[0] = lo; w[1] = __byte_perm(lo, mid, 0x5432); w[2] = mid; w[3] = __byte_perm(mid, hi, 0x5432);
                     }
-                    const uint32_t p0[2] = { (w0[1] & keep) | one, (w0[2] & keep) | one };
-                    const uint32_t p2[2] = { (w2[1] & keep) | one, (w2[2] & keep) | one };
+#pragma unroll
+                    for (int t = 0; t < 4; t++) wh[t] = (wh[t] & keep) | one;
 #pragma unroll
                     for (int m = 0; m < 2; m++) {
                         const uint4 A = m ? T1 : T0;
+                        int d[4][4];
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            int da[4], db[4];
-                            mma_u8u8_16832(da, A.x, A.y, A.z, A.w, w0[u], p0[u]);
-                            mma_u8u8_16832(db, A.x, A.y, A.z, A.w, w2[u], p2[u]);
-                            t32[(16 * m + g4) * 12 + 4 * u + q4] = word(da, db, 0);
-                            t32[(16 * m + g4 + 8) * 12 + 4 * u + q4] = word(da, db, 1);
-                        }
+                        for (int t = 0; t < 4; t++) mma_u8u8_16832(d[t], A.x, A.y, A.z, A.w, wl[t], wh[t]);
+                        *reinterpret_cast<uint2*>(orow + (16 * m) * 32) = make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0));
+                        *reinterpret_cast<uint2*>(orow + (16 * m + 8) * 32) = make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1));
                     }
                 } else {
                     // A = Hankel windows of the left reference (rows y = 16m + g, g + 8), B = W^T from the table
@@ -318,22 +318,15 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
                     for (int j = 0; j < 4; j++) wpat[j] = (win[j + 2] & keep) | one;
 #pragma unroll
                     for (int m = 0; m < 2; m++) {
-#pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            const uint4 B = u ? T1 : T0;
-                            int da[4], db[4];
-                            mma_u8u8_16832(da, win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], B.x, B.y);
-                            mma_u8u8_16832(db, win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], B.z, B.w);
-                            t32[(16 * m + g4) * 12 + 4 * u + q4] = word(da, db, 0);
-                            t32[(16 * m + g4 + 8) * 12 + 4 * u + q4] = word(da, db, 1);
-                        }
+                        int d[4][4];
+                        mma_u8u8_16832(d[0], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T0.x, T0.y);
+                        mma_u8u8_16832(d[1], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T0.z, T0.w);
+                        mma_u8u8_16832(d[2], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T1.x, T1.y);
+                        mma_u8u8_16832(d[3], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T1.z, T1.w);
+                        *reinterpret_cast<uint2*>(orow + (16 * m) * 32) = make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0));
+                        *reinterpret_cast<uint2*>(orow + (16 * m + 8) * 32) = make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1));
                     }
                 }
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < 2; it++)
-                    reinterpret_cast<uint4*>(out)[it * 32 + lane] =
-                        *reinterpret_cast<const uint4*>(&tile[warp][(16 * it + (lane >> 1)) * 48 + 16 * (lane & 1)]);
                 __syncwarp();
                 continue;
             }
