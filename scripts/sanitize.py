@@ -51,8 +51,11 @@ for R, (w, h) in ((3, (40, 24)), (8, (200, 24)), (32, (200, 16))):
 xb.tune(1, 0)
 refs = rng.integers(0, 256, (70, 129)).astype(np.uint8)
 modes = np.tile(np.arange(35, dtype=np.uint8), 2)
-pred = xb.xIntra32Pred(refs, modes)
-check("intra32", all(np.array_equal(pred[i], o.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))) for i in range(70)))
+for swar in (0, 1):                              # 0 = tensor-core angular path (shipped), 1 = CUDA-core SWAR interpolation
+    xb.tune(8, swar)
+    pred = xb.xIntra32Pred(refs, modes)
+    check(f"intra32 swar={swar}", all(np.array_equal(pred[i], o.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))) for i in range(70)))
+xb.tune(8, 0)
 w, h = 96, 64
 fr = lambda: o.conv_input_fmt(rng.integers(0, 256, (h, w)).astype(np.uint8), rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8), rng.integers(0, 256, (h // 2, w // 2)).astype(np.uint8))
 a, b = fr(), fr()
