@@ -386,7 +386,7 @@ def main():
             hbm(f"dct{1 << log2n}_blocks_per_s", ns >> (2 * log2n), 4 << (2 * log2n), ms)
         ms = timed(lambda: xb.xIdct32BatchDev(sp, dp, ns >> 10, 7, 10, st), 10)
         hbm("idct32_blocks_per_s", ns >> 10, 4096, ms, "parity unpinned (no inverse in the reference)")
-        npred = 1 << 19
+        npred = 1 << 20
         refs = torch.randint(0, 256, (npred, 129), device=dev, generator=g, dtype=torch.uint8)
         modes = (torch.arange(npred, device=dev) % 35).to(torch.uint8)
         pred = torch.empty((npred, 1024), device=dev, dtype=torch.uint8)
