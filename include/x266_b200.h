@@ -152,6 +152,10 @@ int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8_t* dPred, 
  *   bestMode[i] = argmin_m cost[i][m] (ties -> lowest mode).  Prediction and residual never leave the SM. */
 int xIntra32Decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n);
 int xIntra32DecideDev(const uint8_t* dCur, const uint8_t* dRefs, uint32_t* dCost, int32_t* dBestMode, size_t n, void* stream);
+/* Diagnostic (host only, needs no device): the per-mode MMA fragment table the intra kernel multiplies with, 35 x 256 words,
+ * [mode][half][lane][4] -- A fragments of the weight matrix for vertical modes, B fragments of its transpose (output columns
+ * permuted, x = 8(n>>1) + 2t + (n&1)) for horizontal modes.  tests/intra_mma_model.py replays the kernel's choreography with it. */
+int xIntra32MmaTable(uint32_t* table /* [35 * 256] */);
 
 /* ================================================================================================
  * "Next" rows: the encoder's tiled frame stores on the device.

@@ -260,3 +260,25 @@ def test_search_golden_pins_oracle_search(orc):
         cost, best = orc.satd_search(cur, refp, 32, b, b + 1)
         assert np.array_equal(best[0], g["best"][b])
         assert fnv1a64(cost[0]) == int(g["sample_fnv"][k])
+
+
+def test_intra_mma_choreography_with_product_table(orc):
+    """The intra kernel's tensor-core path as a lane-exact numpy model (tests/intra_mma_model.py), multiplied with the fragment
+    table the LIBRARY generates on the host (xIntra32MmaTable needs no device): every fractional angular mode, random and
+    extreme reference samples, arbitrary stale bytes in the strip."""
+    import x266_b200
+    from intra_mma_model import ANG, predict
+    table = x266_b200.xIntra32MmaTable()
+    assert not table[[0, 1, 2, 18, 34]].any()                     # DC / planar / pure-copy modes have no table row
+    r = np.random.default_rng(4)
+    for trial in range(4):
+        raw = r.integers(0, 256, 129).astype(np.uint8)
+        if trial == 0:
+            raw[:] = 255
+        if trial == 1:
+            raw = r.choice([0, 255], 129).astype(np.uint8)
+        garbage = r.integers(0, 256, 128).astype(np.uint8)
+        for mode in range(2, 35):
+            if ANG[mode] & 31 == 0:
+                continue
+            assert np.array_equal(predict(raw, mode, table, garbage), orc.intra32(raw[:64], raw[64:], mode)), (trial, mode)

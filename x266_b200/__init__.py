@@ -14,6 +14,6 @@ from .binding import (  # noqa: F401
     xFrameResiDct32, xFrameResiDct32Dev, xConvInputFmtDev, xConvOutput420Dev,
     xTranspose32x32Batch, xTranspose32x32BatchDev,
     xIntra32Decide, xIntra32DecideDev, xIdct32Batch, xIdct32BatchDev, xDct32BatchMultiGpu,
-    sad, xSad8x8Search, xSad8x8SearchDev,
+    sad, xSad8x8Search, xSad8x8SearchDev, xIntra32MmaTable,
     bdpi_dct_block, bdpi_satd_block, X266Error,
 )

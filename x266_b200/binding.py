@@ -46,6 +46,7 @@ def lib():
     L.xGpuKernelLaunches.restype = C.c_ulonglong
     L.xGpuSetDctVariant.argtypes = [i]
     L.xGpuTune.argtypes = [i, i]
+    L.xIntra32MmaTable.argtypes = [vp]
     L.xDct32Batch.argtypes = [vp, vp, sz, i, i]
     L.xDct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
     L.xDct32BatchMultiGpu.argtypes = [vp, vp, sz, i, i, i]
@@ -92,6 +93,13 @@ def kernel_launches():
 
 def set_dct_variant(v):
     _ck(lib().xGpuSetDctVariant(v), "xGpuSetDctVariant")
+
+
+def xIntra32MmaTable():
+    """host-only: the MMA fragment table of the intra kernel, [35][2][32][4] uint32"""
+    t = np.zeros((35, 2, 32, 4), np.uint32)
+    _ck(lib().xIntra32MmaTable(t.ctypes.data), "xIntra32MmaTable")
+    return t
 
 
 def tune(key, value):

@@ -237,6 +237,13 @@ extern "C" void xGpuFree(void)
 }
 
 extern "C" const char* xGpuLastError(void) { return t_err; }
+
+extern "C" int xIntra32MmaTable(uint32_t* table)
+{
+    if (!table) return fail("xIntra32MmaTable", cudaSuccess);
+    intra_mma_table_copy(table);                 // pure host computation: works without a device
+    return 0;
+}
 extern "C" unsigned long long xGpuKernelLaunches(void) { return g_launches.load(); }
 
 extern "C" int xGpuSetDctVariant(int variant)

@@ -86,6 +86,13 @@ static std::vector<uint32_t> intra_mma_table_host()
     return tab;
 }
 
+// host-side copy for inspection without a device (include/x266_b200.h: xIntra32MmaTable)
+void intra_mma_table_copy(uint32_t* out)
+{
+    const std::vector<uint32_t> h = intra_mma_table_host();
+    for (size_t i = 0; i < h.size(); i++) out[i] = h[i];
+}
+
 static const uint32_t* intra_mma_table_dev(cudaError_t* err)
 {
     static const uint32_t* dTab[64] = {};
