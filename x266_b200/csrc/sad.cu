@@ -2,8 +2,7 @@
 // Reference behaviour: riscv/programs/benchmarks/sad/sad.c:27-38 -- sum over an n x n region of
 // abs((int)a[i*n+j] - (int)b[i*n+j]); golden value 344807 for the shipped 64x64 dataset (dataset1.h:423-426).
 // Both kernels use the native packed-byte VABSDIFF4.U8.ACC (4 |a-b| + accumulate per instruction).
-#include "common.cuh"
-#include "kernels.h"
+#include "search_tile.cuh"
 
 namespace x266 {
 
@@ -102,10 +101,9 @@ sad8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict_
 //      the current block (64 B) is read from shared memory once for both positions: 4 LDS.128 + 32 VABSDIFF4.U8.ACC per
 //      two candidates (v1: 24 LDS.32 + 16 SHF + 16 VABSDIFF4 per candidate, LSU bound).  Argmin as in v3: per (slot,
 //      position) running key in registers, 8-lane shuffle fold, 64-bit atomicMin into a stream-ordered scratch buffer. ----
-constexpr int SAD2_TILE = 64;
+constexpr int SAD2_TILE = SRCH_TILE;
 constexpr int SAD2_WW = 18;                  // window pitch in words (72 bytes)
 constexpr int SAD2_CS = 20;                  // words per current block in smem: 16 + 4 pad (four blocks of a warp on distinct banks)
-template <int R> __host__ __device__ constexpr int sad2_chunks() { return R >= 32 ? 3 : R >= 16 ? 2 : 1; }
 
 template <int R>
 __global__ void __launch_bounds__(32, 16)
@@ -115,7 +113,7 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
     constexpr int SIDE = 2 * R + 1;
     constexpr int NSLOT = R / 4 + 2;
     constexpr int NBLK = R / 4 + 8;
-    constexpr int CH = (SIDE + sad2_chunks<R>() - 1) / sad2_chunks<R>();
+    constexpr int CH = (SIDE + srch_chunks<R>() - 1) / srch_chunks<R>();
     constexpr int WR = CH + 7;
     __shared__ __align__(16) uint32_t win[WR * SAD2_WW];
     __shared__ __align__(16) uint32_t curs[NBLK * SAD2_CS];
@@ -186,7 +184,7 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
             B[2 * r] = __funnelshift_r(x2, x3, sh); B[2 * r + 1] = __funnelshift_r(x3, x4, sh);
         }
         const int dy = my - R;
-        const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
+        const unsigned rank = srch_rank(dy);
         uint32_t* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) {
@@ -225,75 +223,15 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
         }
     }
 
-    if (keys) {
-#pragma unroll
-        for (int s = 0; s < NSLOT; s++) {
-#pragma unroll
-            for (int ab = 0; ab < 2; ab++) {
-                if ((ab == 0 && s > R / 4) || (ab == 1 && s < 1)) continue;
-                const unsigned k32 = ab ? keyB[s] : keyA[s];
-                unsigned long long key = ~0ull;
-                if (k32 != 0xFFFFFFFFu) {
-                    const unsigned rank = k32 & 127u;
-                    const int dy = (rank & 1) ? -(int)((rank + 1) >> 1) : (int)(rank >> 1);
-                    const int mx = e + 2 * R - 8 * s + 8 * ab, dx = mx - R;
-                    key = ((unsigned long long)(k32 >> 7) << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
-                          ((unsigned long long)(dy + R) << 12) | (unsigned long long)mx;
-                }
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                    key = other < key ? other : key;
-                }
-                if (e == 0 && key != ~0ull) atomicMin(&keys[bRow + (iq + s) - blk0], key);
-            }
-        }
-    }
-}
-
-__global__ void sad_keys_decode_kernel(const unsigned long long* __restrict__ keys, int32_t* __restrict__ best, size_t n, int R)
-{
-    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    const unsigned long long k = keys[b];
-    best[3 * b + 0] = (int32_t)(k >> 40);
-    best[3 * b + 1] = (int)(k & 0xFFF) - R;
-    best[3 * b + 2] = (int)((k >> 12) & 0xFFF) - R;
+    if (keys) srch_flush_keys<R, NSLOT>(keyA, keyB, e, (ptrdiff_t)bRow + iq - (ptrdiff_t)blk0, keys);
 }
 
 template <int R>
 static cudaError_t launch_sad_v2(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
                                  uint32_t* cost, int32_t* best, cudaStream_t st)
 {
-    auto kern = sad8x8_search_v2_kernel<R>;
-    const int bw = w / 8;
-    const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
-    const int nPos = 8 * (bw - 1) + 2 * R + 1;
-    const dim3 grid((nPos + SAD2_TILE - 1) / SAD2_TILE, y1 - y0 + 1, sad2_chunks<R>());
-    static bool attrSet[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaError_t e;
-    if (dev < 0 || dev >= 64 || !attrSet[dev]) {
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attrSet[dev] = true;
-    }
-    const size_t nb = blk1 - blk0;
-    unsigned long long* keys = nullptr;
-    if (best) {
-        if ((e = scratch_alloc((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(keys, 0xFF, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
-    }
-    kern<<<grid, 32, 0, st>>>(cur, refPad, strd, w, y0, blk0, blk1, cost, keys);
-    count_launch();
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (best) {
-        sad_keys_decode_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(keys, best, nb, R);
-        count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = scratch_free(keys, st)) != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    struct Tag {};
+    return srch_launch<R>(sad8x8_search_v2_kernel<R>, srch_attr_flag<Tag>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
 }
 
 static int g_sadSearchV1 = 0;

@@ -26,17 +26,15 @@
 // kernel.
 // Pipes (ncu): the integer ALU pipe of sm_100 issues one warp instruction every two cycles, so the 32 VIMNMX.S16x2 per
 // candidate are the floor; the sums therefore go to the FMA pipe (one IDP.2A per word, satd_packed.h maxsum4<1>).
-#include "common.cuh"
-#include "kernels.h"
+#include "search_tile.cuh"
 #include "satd_packed.h"
 
 namespace x266 {
 
-constexpr int S3_TILE = 64;                  // window positions per unit
+constexpr int S3_TILE = SRCH_TILE;           // window positions per unit
 constexpr int S3_WP = 72;                    // window pitch in bytes: 64 positions + 7 halo columns (+1)
 constexpr int S3_TCS = 36;                   // T(cur) row: 32 words + 64*cur[0][0] + pad (16-byte rows, distinct banks for 4 blocks)
 constexpr int S3_CTAS_PER_SM = 16;
-template <int R> constexpr int s3_chunks() { return R >= 32 ? 3 : R >= 16 ? 2 : 1; }   // CTAs per (tile, row): ~22 vertical offsets each
 
 template <int R, int ACCF, int NCH>
 __global__ void __launch_bounds__(32, S3_CTAS_PER_SM)
@@ -76,32 +74,6 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     unsigned keyA[NSLOT], keyB[NSLOT];           // per (slot, position): cost << 7 | rank(my); mx is fixed per entry
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) keyA[s] = keyB[s] = 0xFFFFFFFFu;
-
-    // argmin of this unit: per (slot, position) the best my is known; fold the 8 lanes of a group, then the frame
-    auto flush = [&]() {
-#pragma unroll
-        for (int s = 0; s < NSLOT; s++) {
-#pragma unroll
-            for (int ab = 0; ab < 2; ab++) {
-                if ((ab == 0 && s > R / 4) || (ab == 1 && s < 1)) continue;
-                const unsigned k32 = ab ? keyB[s] : keyA[s];
-                unsigned long long key = ~0ull;
-                if (k32 != 0xFFFFFFFFu) {
-                    const unsigned rank = k32 & 127u;
-                    const int dy = (rank & 1) ? -(int)((rank + 1) >> 1) : (int)(rank >> 1);
-                    const int mx = e + 2 * R - 8 * s + 8 * ab, dx = mx - R;
-                    key = ((unsigned long long)(k32 >> 7) << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
-                          ((unsigned long long)(dy + R) << 12) | (unsigned long long)mx;
-                }
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                    key = other < key ? other : key;
-                }
-                if (e == 0 && key != ~0ull) atomicMin(&keys[bRow + (iq + s) - blk0], key);
-            }
-        }
-    };
 
     // ---- stage the window rows of this chunk, the current blocks and T(cur)
     {
@@ -189,7 +161,7 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
         const uint32_t subA = 64u * wrow[xa] + 2u * s3::BIAS_SUM - 2u;
         const uint32_t subB = 64u * wrow[xa + 8] + 2u * s3::BIAS_SUM - 2u;
         const int dy = my - R;
-        const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
+        const unsigned rank = srch_rank(dy);
         // cost index of (slot s, position A) = cbase + s * (SIDE*SIDE - 8); position B: + 8
         uint32_t* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
 
@@ -224,10 +196,10 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
             }
         }
     }
-    if (keys) flush();
+    if (keys) srch_flush_keys<R, NSLOT>(keyA, keyB, e, (ptrdiff_t)bRow + iq - (ptrdiff_t)blk0, keys);
 }
 
-__global__ void search_keys_decode_kernel(const unsigned long long* __restrict__ keys, int32_t* __restrict__ best, size_t n, int R)
+__global__ void srch_keys_decode_kernel(const unsigned long long* __restrict__ keys, int32_t* __restrict__ best, size_t n, int R)
 {
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
@@ -240,40 +212,12 @@ __global__ void search_keys_decode_kernel(const unsigned long long* __restrict__
 static int g_accForm = 1;
 void set_search_acc_form(int f) { g_accForm = f; }
 
-template <int R, int ACCF, int NCH = s3_chunks<R>()>
+template <int R, int ACCF>
 static cudaError_t launch_v3f(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
                               uint32_t* cost, int32_t* best, cudaStream_t st)
 {
-    auto kern = satd8x8_search_v3_kernel<R, ACCF, NCH>;
-    const int bw = w / 8;
-    const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
-    const int nPos = 8 * (bw - 1) + 2 * R + 1;
-    const int nTiles = (nPos + S3_TILE - 1) / S3_TILE;
-    static bool attrSet[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaError_t e;
-    if (dev < 0 || dev >= 64 || !attrSet[dev]) {
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attrSet[dev] = true;
-    }
-    const dim3 grid(nTiles, y1 - y0 + 1, NCH);
-    const size_t nb = blk1 - blk0;
-    unsigned long long* keys = nullptr;
-    if (best) {
-        if ((e = scratch_alloc((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(keys, 0xFF, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
-    }
-    kern<<<grid, 32, 0, st>>>(cur, refPad, strd, w, y0, blk0, blk1, cost, keys);
-    count_launch();
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (best) {
-        search_keys_decode_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(keys, best, nb, R);
-        count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = scratch_free(keys, st)) != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    struct Tag {};
+    return srch_launch<R>(satd8x8_search_v3_kernel<R, ACCF, srch_chunks<R>()>, srch_attr_flag<Tag>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
 }
 
 template <int R>
