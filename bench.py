@@ -335,8 +335,15 @@ def main():
         for name, fn in (("satd8x8_search_candidates_per_s", xb.xSatd8x8SearchDev), ("sad8x8_search_candidates_per_s", xb.xSad8x8SearchDev)):
             ms = timed(lambda: fn(cur.data_ptr(), refp.data_ptr(), w + 2 * rg, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st), 5)
             cands = nb * 65 * 65
+            # the bound that applies: the integer ALU pipe issues one warp instruction per two cycles per SM sub-partition;
+            # a SATD candidate needs 32 VIMNMX.S16x2 on it, a SAD candidate 16 VABSDIFF4 -- nothing else counted
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            clk_hz = torch.cuda.get_device_properties(dev).clock_rate * 1e3 if hasattr(torch.cuda.get_device_properties(dev), "clock_rate") else 1.965e9
+            alu_peak = sms * 4 * clk_hz / 2 * 32 / (32 if name.startswith("satd") else 16)
             secondary.append({"metric": name, "value": world * cands / (ms * 1e-3), "n_gpus": world, "ms_per_frame": ms,
                               "cpu_baseline": satd_cpu if name.startswith("satd") else None,
+                              "alu_pipe_bound": {"peak": alu_peak, "unit": "candidates/s per GPU", "frac": cands / (ms * 1e-3) / alu_peak,
+                                                 "model": "32 VIMNMX.S16x2 (SATD) / 16 VABSDIFF4 (SAD) per candidate, 1 ALU warp instruction per 2 cycles per sub-partition"},
                               "config": "config3: 1920x1080 per GPU, +-32, u32 cost surface + argmin",
                               "roofline": {"bound": "integer ALU pipe / shared memory (not HBM; SURVEY 8(d))", "achieved": 551903296 / (ms * 1e-3) / 1e9,
                                            "peak": peak, "unit": "GB/s", "frac": 551903296 / (ms * 1e-3) / 1e9 / peak, "traffic": None}})

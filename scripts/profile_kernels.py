@@ -42,5 +42,7 @@ for _ in range(2):
 xb.tune(1, 1)
 xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
 xb.tune(1, 0)
+for _ in range(2):
+    xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
 torch.cuda.synchronize()
 print("profile driver done")
