@@ -10,8 +10,8 @@
 //     T(cur) is 128 B and every butterfly of the transform is ONE plain 32-bit add for two coefficients;
 //   * a thread owns TWO window positions (p, p+8) that share 8 of their 9 blocks, so one T(cur) word fetched
 //     from shared memory serves two candidates: 64 B of shared-memory traffic per candidate instead of 256;
-//   * |a-b| = 2 max(a,b) - a - b with sum_k T[k] = 64 x[0][0]: per pair of coefficients one VIMNMX.S16x2, a
-//     quarter of an add and an eighth of an IDP.2A, instead of two VABSDIFF.
+//   * |a-b| = 2 max(a,b) - a - b with sum_k T[k] = 64 x[0][0]: per pair of coefficients one VIMNMX.S16x2 (integer ALU
+//     pipe) and one IDP.2A (FMA pipe) instead of two VABSDIFF on the ALU pipe.
 // Work decomposition: a unit is (row of 8x8 blocks, tile of 64 horizontal window positions, third of the 2R+1 vertical
 // offsets); ONE WARP = one CTA owns a unit: the window rows it touches (22+7 rows x 72 bytes at R=32) and the T(cur) of
 // the R/4+8 blocks it can serve live in its 6.6 KB of shared memory, 16 such CTAs are resident per SM, and nothing in
@@ -21,7 +21,7 @@
 // Lane (g, e) = (lane>>3, lane&7) owns positions P0+16g+e and P0+16g+8+e; with q = P0/8+2g the blocks of "slot" s are
 // i = q-R/4+s for both positions (mx = e+2R-8s and e+2R+8-8s), so the eight lanes of a group read the same T(cur) and
 // write 32 contiguous bytes of the cost surface.  Tiles follow window positions, not blocks, so no lane is wasted on
-// a strip edge (v2: 38 %).  A block's candidates span up to three tiles and five chunks: the argmin is combined with
+// a strip edge (v2: 38 %).  A block's candidates span up to three tiles and three chunks: the argmin is combined with
 // 64-bit atomicMin keys (cost, mvx^2+mvy^2, my, mx) in a stream-ordered scratch buffer and decoded by a second tiny
 // kernel.
 // Pipes (ncu): the integer ALU pipe of sm_100 issues one warp instruction every two cycles, so the 32 VIMNMX.S16x2 per
