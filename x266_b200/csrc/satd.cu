@@ -612,11 +612,16 @@ satd8x8_imma2_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out
             if (t == 0) mma_u8s8(el, BLo, B[t][0], B[t][1], cFix);
             else mma_u8s8(el, BLo, B[t][0], B[t][1], cZero);
             mma_s8s8(eh, BHi, B[t][0], B[t][1], cZero);
-            // lo + 256*hi, sign-extend the low 16 bits (one PRMT with sign replication), |.| accumulate
-            s0a = __sad((int)prmt(dl[0] + dh[0] * 256, 0, 0x9910), 0, s0a); s0b = __sad((int)prmt(dl[1] + dh[1] * 256, 0, 0x9910), 0, s0b);
-            s1a = __sad((int)prmt(dl[2] + dh[2] * 256, 0, 0x9910), 0, s1a); s1b = __sad((int)prmt(dl[3] + dh[3] * 256, 0, 0x9910), 0, s1b);
-            s0a = __sad((int)prmt(el[0] + eh[0] * 256, 0, 0x9910), 0, s0a); s0b = __sad((int)prmt(el[1] + eh[1] * 256, 0, 0x9910), 0, s0b);
-            s1a = __sad((int)prmt(el[2] + eh[2] * 256, 0, 0x9910), 0, s1a); s1b = __sad((int)prmt(el[3] + eh[3] * 256, 0, 0x9910), 0, s1b);
+            // lo + 256*hi (IMAD); the int16 coefficient is the low half (= the reference's wrap, satd.c:35).  Two coefficients are packed
+            // into one word and |.| is max(x, -x) on both halves (LOP3 + VIADDMNMX.S16x2; -32768 stays 0x8000 = 32768 unsigned, as
+            // abs() of the widened value gives in C); IDP.2A adds the two unsigned halves to the accumulator on the FMA pipe:
+            // 3 ALU + 3 FMA instructions per coefficient pair instead of 4 + 2 -- the ALU pipe is the busier one here.
+            auto abs2 = [](int lo0, int hi0, int lo1, int hi1, unsigned acc) {
+                const uint32_t x = prmt((uint32_t)(lo0 + hi0 * 256), (uint32_t)(lo1 + hi1 * 256), 0x5410);
+                return __dp2a_lo(__vmaxs2(x, __vneg2(x)), 0x0101u, acc);
+            };
+            s0a = abs2(dl[0], dh[0], dl[1], dh[1], s0a); s1a = abs2(dl[2], dh[2], dl[3], dh[3], s1a);
+            s0b = abs2(el[0], eh[0], el[1], eh[1], s0b); s1b = abs2(el[2], eh[2], el[3], eh[3], s1b);
         }
         unsigned sad0 = s0a + s0b, sad1 = s1a + s1b;
         sad0 += __shfl_xor_sync(0xffffffffu, sad0, 1); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 1);
