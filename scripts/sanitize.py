@@ -30,7 +30,7 @@ for log2n, sh in ((2, (1, 8)), (3, (2, 9)), (4, (3, 10))):
 xb.tune(3, 0)
 check("partialButterfly32", np.array_equal(xb.partialButterfly32(x[:77 * 32], 4, 77), o.partial(x[:77 * 32], 4, 77)))
 d = o.residual(1003 * 64, 3, 2)
-for v in (0, 1, 2, 3):
+for v in (0, 1, 2, 3, 4, 5):
     xb.tune(2, v)
     check(f"satd batch variant={v}", np.array_equal(xb.xSatd8x8Batch(d), o.satd(d)))
 xb.tune(2, 0)

@@ -179,9 +179,12 @@ def test_config4_mixed_partition(x266, orc):
 
 
 # ---------------------------------------------------------------------------------------- SATD
-@pytest.fixture(params=["imma-v2", "cuda-core", "imma-v1", "imma-v2-3cta"])
+SATD_VARIANTS = ["imma-v2-ring3", "cuda-core", "imma-v1", "imma-v2-3cta", "imma-v2-direct", "imma-v2-ring4"]
+
+
+@pytest.fixture(params=SATD_VARIANTS)
 def satd_variant(request, x266):
-    x266.tune(2, ["imma-v2", "cuda-core", "imma-v1", "imma-v2-3cta"].index(request.param))
+    x266.tune(2, SATD_VARIANTS.index(request.param))
     yield request.param
     x266.tune(2, 0)
 

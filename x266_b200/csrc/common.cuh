@@ -50,6 +50,14 @@ __device__ __forceinline__ void st_global_stream(void* p, uint4 v)
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// per-thread asynchronous 16-byte copy global -> shared (LDGSTS), L1 bypassed; groups complete in order
+__device__ __forceinline__ void cp_async16(uint32_t smemAddr, const void* g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smemAddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr)
 {
     uint4 r;

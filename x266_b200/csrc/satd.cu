@@ -634,7 +634,113 @@ satd8x8_imma2_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out
     }
 }
 
-static int g_satdCuda = 0;      // tuning/diagnostic: 0 = IMMA v2 (H2 (x) H32 fold, 16 IMMA per unit), 1 = CUDA-core kernel, 2 = IMMA v1 (32 IMMA per unit), 3 = IMMA v2 at 3 CTAs/SM
+template <int MINB, int ST>
+__global__ void __launch_bounds__(SATDI_WARPS * 32, MINB)
+satd8x8_imma3_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+
+    // H32 fragments: K position 16r+4q+i <-> sample 8q+4r+i (of the 32 folded samples), column n' = 8t+g
+    uint32_t B[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int pix = 8 * q + 4 * r + i, nn = 8 * t + g;
+                v |= ((__popc(nn & pix) & 1) ? 0xFFu : 0x01u) << (8 * i);
+            }
+            B[t][r] = v;
+        }
+    const int cZero[4] = { 0, 0, 0, 0 };
+    // +32 on bottom-half coefficient 0 (tile 0, column 0 = lanes with q == 0, accumulator slots 0 and 2)
+    const int cFix[4] = { q == 0 ? 32 : 0, 0, q == 0 ? 32 : 0, 0 };
+
+    const size_t nUnits = (n + 15) / 16;
+    const size_t first = (size_t)blockIdx.x * SATDI_WARPS + warp;
+    const size_t stride = (size_t)gridDim.x * SATDI_WARPS;
+
+    // ST-deep ring of 2 KiB units per warp, filled by per-lane 16-byte asynchronous copies (LDGSTS): every lane reads back only what
+    // it copied itself, so completion needs no barrier beyond cp.async.wait_group, and the bytes in flight no longer cost registers
+    extern __shared__ __align__(16) uint4 ring[];                 // [warp][stage][chunk 0..3][lane]
+    const uint32_t ringBase = smem_u32(ring) + (uint32_t)(warp * ST * 4 * 32 + lane) * 16;
+    auto issue_unit = [&](size_t u, int stg) {
+        if (u < nUnits) {
+            size_t c0 = u * 16 + g, c1 = c0 + 8;
+            c0 = c0 < n ? c0 : n - 1;
+            c1 = c1 < n ? c1 : n - 1;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                cp_async16(ringBase + (uint32_t)((stg * 4 + 2 * s) * 32) * 16, diff + c0 * 64 + 32 * s + 8 * q);
+                cp_async16(ringBase + (uint32_t)((stg * 4 + 2 * s + 1) * 32) * 16, diff + c1 * 64 + 32 * s + 8 * q);
+            }
+        }
+        cp_async_commit();                                       // one group per unit slot, empty past the end
+    };
+#pragma unroll
+    for (int k = 0; k < ST - 1; k++) issue_unit(first + (size_t)k * stride, k);
+    int stg = 0;
+
+    for (size_t u = first; u < nUnits; u += stride) {
+        // fold bit 5, then byte planes.  Fragment registers: [0] row g K 4q+i, [1] row g+8, [2] row g K 16+4q+i, [3] row g+8
+        uint32_t TL[4], TH[4], BLo[4], BHi[4];
+#pragma unroll
+        cp_async_wait<ST - 2>();                                 // the oldest group (this unit) has landed
+        uint4 cur4[2][2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            cur4[s][0] = ld_shared_v4(ringBase + (uint32_t)((stg * 4 + 2 * s) * 32) * 16);
+            cur4[s][1] = ld_shared_v4(ringBase + (uint32_t)((stg * 4 + 2 * s + 1) * 32) * 16);
+        }
+        issue_unit(u + (size_t)(ST - 1) * stride, (stg + ST - 1) % ST);
+        stg = (stg + 1) % ST;
+#pragma unroll
+        for (int row = 0; row < 2; row++) {
+            const uint4 a = cur4[0][row], b = cur4[1][row];
+            const uint32_t tx = vadd16x2(a.x, b.x), ty = vadd16x2(a.y, b.y), tz = vadd16x2(a.z, b.z), tw = vadd16x2(a.w, b.w);
+            const uint32_t bx = vadd16x2(a.x, ~b.x), by = vadd16x2(a.y, ~b.y), bz = vadd16x2(a.z, ~b.z), bw = vadd16x2(a.w, ~b.w);
+            TL[row] = prmt(tx, ty, 0x6420);      TH[row] = prmt(tx, ty, 0x7531);
+            TL[2 + row] = prmt(tz, tw, 0x6420);  TH[2 + row] = prmt(tz, tw, 0x7531);
+            BLo[row] = prmt(bx, by, 0x6420);     BHi[row] = prmt(bx, by, 0x7531);
+            BLo[2 + row] = prmt(bz, bw, 0x6420); BHi[2 + row] = prmt(bz, bw, 0x7531);
+        }
+
+        unsigned s0a = 0, s0b = 0, s1a = 0, s1b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            int dl[4], dh[4], el[4], eh[4];
+            mma_u8s8(dl, TL, B[t][0], B[t][1], cZero);
+            mma_s8s8(dh, TH, B[t][0], B[t][1], cZero);
+            if (t == 0) mma_u8s8(el, BLo, B[t][0], B[t][1], cFix);
+            else mma_u8s8(el, BLo, B[t][0], B[t][1], cZero);
+            mma_s8s8(eh, BHi, B[t][0], B[t][1], cZero);
+            // lo + 256*hi (IMAD); the int16 coefficient is the low half (= the reference's wrap, satd.c:35).  Two coefficients are packed
+            // into one word and |.| is max(x, -x) on both halves (LOP3 + VIADDMNMX.S16x2; -32768 stays 0x8000 = 32768 unsigned, as
+            // abs() of the widened value gives in C); IDP.2A adds the two unsigned halves to the accumulator on the FMA pipe:
+            // 3 ALU + 3 FMA instructions per coefficient pair instead of 4 + 2 -- the ALU pipe is the busier one here.
+            auto abs2 = [](int lo0, int hi0, int lo1, int hi1, unsigned acc) {
+                const uint32_t x = prmt((uint32_t)(lo0 + hi0 * 256), (uint32_t)(lo1 + hi1 * 256), 0x5410);
+                return __dp2a_lo(__vmaxs2(x, __vneg2(x)), 0x0101u, acc);
+            };
+            s0a = abs2(dl[0], dh[0], dl[1], dh[1], s0a); s1a = abs2(dl[2], dh[2], dl[3], dh[3], s1a);
+            s0b = abs2(el[0], eh[0], el[1], eh[1], s0b); s1b = abs2(el[2], eh[2], el[3], eh[3], s1b);
+        }
+        unsigned sad0 = s0a + s0b, sad1 = s1a + s1b;
+        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 1); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 1);
+        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 2); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 2);
+        if (q == 0) {
+            const size_t c0 = u * 16 + g;
+            if (c0 < n) out[c0] = (int)((sad0 + 2) >> 2);
+            if (c0 + 8 < n) out[c0 + 8] = (int)((sad1 + 2) >> 2);
+        }
+    }
+}
+
+static int g_satdCuda = 0;      // tuning/diagnostic: 0 = IMMA v2 fed by a 3-stage cp.async ring (shipped), 1 = CUDA-core kernel, 2 = IMMA v1 (32 IMMA per unit),
+                                // 3 = IMMA v2 register double-buffered at 3 CTAs/SM, 4 = the same at 2 CTAs/SM, 5 = ring with 4 stages
 void set_satd_cuda_cores(int on) { g_satdCuda = on; }
 
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st)
@@ -644,7 +750,20 @@ cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cu
         size_t want = ((n + 15) / 16 + SATDI_WARPS - 1) / SATDI_WARPS;
         size_t cap = (size_t)sm_count() * (g_satdCuda == 3 ? 3 : 2);
         const int grid = (int)(want < cap ? want : cap);
-        if (g_satdCuda == 2) satd8x8_imma_kernel<2, 1><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
+        if (g_satdCuda == 0 || g_satdCuda == 5) {                 // shipped: cp.async ring, 3 stages (5: 4 stages)
+            constexpr int smem3 = SATDI_WARPS * 3 * 2048, smem4 = SATDI_WARPS * 4 * 2048;
+            static bool attrSet4[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (g_satdCuda == 5 && (dev < 0 || dev >= 64 || !attrSet4[dev])) {
+                cudaError_t e = cudaFuncSetAttribute(satd8x8_imma3_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
+                if (e != cudaSuccess) return e;
+                if (dev >= 0 && dev < 64) attrSet4[dev] = true;
+            }
+            if (g_satdCuda == 5) satd8x8_imma3_kernel<2, 4><<<grid, SATDI_WARPS * 32, smem4, st>>>(diff, out, n);
+            else satd8x8_imma3_kernel<2, 3><<<grid, SATDI_WARPS * 32, smem3, st>>>(diff, out, n);
+        }
+        else if (g_satdCuda == 2) satd8x8_imma_kernel<2, 1><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
         else if (g_satdCuda == 3) satd8x8_imma2_kernel<3><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
         else satd8x8_imma2_kernel<2><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
         count_launch();
