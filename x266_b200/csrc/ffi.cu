@@ -76,6 +76,23 @@ int sm_count()
     return g_smCache[dev];
 }
 
+int resident_ctas_per_sm(const void* kernel, int blockThreads, size_t dynSmemBytes)
+{
+    struct Entry { const void* k; int dev; int block; int n; };
+    static Entry cache[256];
+    static int used = 0;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    std::lock_guard<std::mutex> lk(mu);
+    for (int i = 0; i < used; i++)
+        if (cache[i].k == kernel && cache[i].dev == dev && cache[i].block == blockThreads) return cache[i].n;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, blockThreads, dynSmemBytes) != cudaSuccess || n < 1) n = 1;
+    if (used < 256) cache[used++] = Entry{ kernel, dev, blockThreads, n };
+    return n;
+}
+
 static cudaMemPool_t g_pool[MAX_DEV] = {};
 static std::mutex g_poolMu;
 
@@ -264,6 +281,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 6) { set_search_acc_form(value); return 0; }
     if (key == 7) { set_sad_search_v1(value); return 0; }
     if (key == 8) { set_intra_swar(value); return 0; }
+    if (key == 9) { set_intra_ctas(value); return 0; }
     if (key == 4 && value >= 0) { g_dctChunk.store((size_t)value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }

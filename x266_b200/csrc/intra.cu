@@ -685,13 +685,16 @@ void set_decide_v1(int on) { g_decideV1 = on; }
 cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    const size_t cap = (size_t)sm_count() * 4;
+    const void* kern = g_decideV1 ? (const void*)intra32_decide_kernel : (const void*)intra32_decide_v2_kernel;
+    const size_t cap = (size_t)sm_count() * resident_ctas_per_sm(kern, IDEC_WARPS * 32, 0);
     if (g_decideV1) intra32_decide_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
     else intra32_decide_v2_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
     count_launch();
     return cudaGetLastError();
 }
 
+static int g_intraCtas = 0;      // tuning/diagnostic: CTAs per SM of the persistent grid (0 = 8)
+void set_intra_ctas(int v) { g_intraCtas = v; }
 static int g_intraSwar = 0;      // tuning/diagnostic: 1 = CUDA-core SWAR interpolation for every angular mode
 void set_intra_swar(int on) { g_intraSwar = on; }
 
@@ -700,7 +703,10 @@ cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pr
     if (n == 0) return cudaSuccess;
     if (n > ((size_t)1 << 31)) return cudaErrorInvalidValue;          // 32-bit prediction index in the kernel (2 TiB of output)
     const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
-    const size_t cap = (size_t)sm_count() * 8;
+    const bool aligned4 = (reinterpret_cast<uintptr_t>(refs) & 3) == 0;
+    const int perSm = g_intraCtas > 0 ? g_intraCtas
+                                      : resident_ctas_per_sm(aligned4 ? (const void*)intra32_kernel<true> : (const void*)intra32_kernel<false>, INTRA_WARPS * 32, 0);
+    const size_t cap = (size_t)sm_count() * perSm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     cudaError_t e;
     const uint32_t* tab = intra_mma_table_dev(&e);

@@ -7,6 +7,10 @@
 namespace x266 {
 
 int sm_count();                 // SMs of the current device (cached per device)
+// CTAs of `kernel` that are resident per SM at this block size (cudaOccupancyMaxActiveBlocksPerMultiprocessor, cached per kernel
+// and device).  Persistent grids are sized with it: a grid larger than what is resident runs a second, under-filled wave (measured on
+// the intra kernel: 8 CTAs/SM requested, 5 resident -> 8 % slower than 5 or 10).
+int resident_ctas_per_sm(const void* kernel, int blockThreads, size_t dynSmemBytes);
 // Stream-ordered scratch memory from a library-owned pool of the current device (release threshold = keep: a
 // synchronisation between two calls must not hand the memory back to the driver and re-allocate it on the next call).
 cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st);
@@ -39,6 +43,7 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
 cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                      size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
 void intra_mma_table_copy(uint32_t* out);   // 35 x 256 words: the per-mode MMA fragment table of the intra kernel (host copy)
+void set_intra_ctas(int v);       // tuning/diagnostic: CTAs per SM of the intra kernel's persistent grid
 void set_intra_swar(int on);      // tuning/diagnostic: CUDA-core SWAR interpolation instead of the tensor-core angular path
 void set_sad_search_v1(int on);   // tuning/diagnostic: first-generation SAD search (one CTA per block)
 void set_search_acc_form(int f);  // tuning/diagnostic: accumulate form of the v3 search (satd_packed.h maxsum4)
