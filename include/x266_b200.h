@@ -86,7 +86,7 @@ int xGpuSetDctVariant(int variant);
  * key 0 IMMA DCT32 instantiation (warps, stages, CTAs/SM, staging; scripts/tune_dct.py) | 1 SATD search kernel (0 v3 packed
  * transform domain, 1 one CTA per block, 2/3 v2 strips) | 2 SATD batch variant | 3 CUDA-core DCT 8/16 | 4 blocks per chunk of the
  * host-pointer DCT pipeline | 5 CUDA-core intra decision | 6 accumulate form of the v3 search | 7 first-generation SAD search | 8 CUDA-core SWAR intra interpolation |
- * 9 CTAs per SM of the intra kernel's persistent grid (0 = what is resident). */
+ * 9 / 10 / 11 CTAs per SM of the intra / DCT8 / DCT4 persistent grids (0 = shipped). */
 int xGpuTune(int key, int value);
 
 /* 2-D forward 32x32 transform of nBlocks contiguous row-major int16 blocks:

@@ -330,6 +330,10 @@ dct4_xchg_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+static int g_dct4Ctas = 0;       // tuning/diagnostic: CTAs per SM of dct4_xchg's persistent grid (0 = 12: measured 4/6/8/10/12/16 ->
+                                 // 5829/5681/6124/6065/6357/6338 GB/s on 1 Gi samples, scripts/time_small_dct_grid.py)
+void set_dct4_ctas(int v) { g_dct4Ctas = v; }
+
 static int grid_for(size_t units, int unitsPerCta, int ctasPerSm)
 {
     size_t want = (units + unitsPerCta - 1) / unitsPerCta;
@@ -363,7 +367,7 @@ cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlo
     if (log2n == 4 && g_smallCuda != 1) return launch_dct16_imma(src, dst, nBlocks, s1, s2, st);
     if (log2n == 3 && g_smallCuda != 1) return launch_dct8_imma(src, dst, nBlocks, s1, s2, st);
     if (log2n == 2 && g_smallCuda == 0) {
-        dct4_xchg_kernel<<<grid_for((nBlocks + 63) / 64, DCT4X_WARPS, 8), DCT4X_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
+        dct4_xchg_kernel<<<grid_for((nBlocks + 63) / 64, DCT4X_WARPS, g_dct4Ctas > 0 ? g_dct4Ctas : 12), DCT4X_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
         count_launch();
         return cudaGetLastError();
     }

@@ -413,11 +413,14 @@ dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
     }
 }
 
+static int g_dct8Ctas = 0;       // tuning/diagnostic: CTAs per SM of the persistent grid (0 = 2)
+void set_dct8_ctas(int v) { g_dct8Ctas = v; }
+
 cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
 {
     if (nBlocks == 0) return cudaSuccess;
     const size_t want = ((nBlocks + 15) / 16 + D8_WARPS - 1) / D8_WARPS;
-    const size_t cap = (size_t)sm_count() * 2;
+    const size_t cap = (size_t)sm_count() * (g_dct8Ctas > 0 ? g_dct8Ctas : 2);
     dct8_imma_kernel<<<(int)(want < cap ? want : cap), D8_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
     count_launch();
     return cudaGetLastError();

@@ -282,6 +282,8 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 7) { set_sad_search_v1(value); return 0; }
     if (key == 8) { set_intra_swar(value); return 0; }
     if (key == 9) { set_intra_ctas(value); return 0; }
+    if (key == 10) { set_dct8_ctas(value); return 0; }
+    if (key == 11) { set_dct4_ctas(value); return 0; }
     if (key == 4 && value >= 0) { g_dctChunk.store((size_t)value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }

@@ -43,6 +43,8 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
 cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                      size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
 void intra_mma_table_copy(uint32_t* out);   // 35 x 256 words: the per-mode MMA fragment table of the intra kernel (host copy)
+void set_dct8_ctas(int v);        // tuning/diagnostic: CTAs per SM of the dct8 / dct4 persistent grids
+void set_dct4_ctas(int v);
 void set_intra_ctas(int v);       // tuning/diagnostic: CTAs per SM of the intra kernel's persistent grid
 void set_intra_swar(int on);      // tuning/diagnostic: CUDA-core SWAR interpolation instead of the tensor-core angular path
 void set_sad_search_v1(int on);   // tuning/diagnostic: first-generation SAD search (one CTA per block)
