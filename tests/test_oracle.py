@@ -282,3 +282,34 @@ def test_intra_mma_choreography_with_product_table(orc):
             if ANG[mode] & 31 == 0:
                 continue
             assert np.array_equal(predict(raw, mode, table, garbage), orc.intra32(raw[:64], raw[64:], mode)), (trial, mode)
+
+
+@pytest.mark.parametrize("R", [8, 16, 32])
+@pytest.mark.parametrize("bw", [1, 5, 9, 25, 240])
+def test_search_tile_decomposition_covers_every_candidate_once(R, bw):
+    """The position-tile decomposition of the full-search kernels (x266_b200/csrc/search_tile.cuh): tiles of 64 window positions,
+    lane (g, e) owns positions P0+16g+e (A) and +8 (B), slot s serves block q-R/4+s with mx = e+2R-8s (A) / e+2R+8-8s (B), A for
+    s <= R/4 (s = 0 only e == 0), B for s >= 1 (s = 1 only e == 0).  Every (block, mx) of a block row must be produced exactly once,
+    by a position that is inside the padded reference, and the slot's T(cur) index 2g+s must stay inside the R/4+8 staged blocks."""
+    nslot, nblk = R // 4 + 2, R // 4 + 8
+    npos = 8 * (bw - 1) + 2 * R + 1
+    seen = {}
+    for tile in range((npos + 63) // 64):
+        P0 = tile * 64
+        for lane in range(32):
+            g, e = lane >> 3, lane & 7
+            iq = P0 // 8 + 2 * g - R // 4
+            for s in range(nslot):
+                i = iq + s
+                if not (0 <= i < bw):
+                    continue
+                assert 0 <= 2 * g + s < nblk
+                if s <= R // 4 and (s >= 1 or e == 0):
+                    mx, p = e + 2 * R - 8 * s, P0 + 16 * g + e
+                    assert p - 8 * i == mx and 0 <= mx <= 2 * R and p < npos
+                    seen[(i, mx)] = seen.get((i, mx), 0) + 1
+                if s >= 1 and (s >= 2 or e == 0):
+                    mx, p = e + 2 * R + 8 - 8 * s, P0 + 16 * g + 8 + e
+                    assert p - 8 * i == mx and 0 <= mx <= 2 * R and p < npos
+                    seen[(i, mx)] = seen.get((i, mx), 0) + 1
+    assert len(seen) == bw * (2 * R + 1) and set(seen.values()) == {1}
