@@ -61,10 +61,15 @@ int satd8x8(const int16_t diff[64]);
 
 /* ================================================================================================
  * Tier 3 -- batched entry points in the style of src/x266.cpp (x-prefixed, int 0/-1).
- * Host-pointer forms copy in/out through an internal chunked, double-buffered stream pipeline
- * (pinned caller memory is DMA'd directly; pageable memory is staged).  *Dev forms take device
- * pointers on the current device plus a cudaStream_t passed as void* (NULL = legacy default
- * stream), enqueue only, and never synchronise.
+ * Host-pointer forms copy in/out through an internal chunked stream pipeline (csrc/ffi.cu: run_chunked).
+ * Caller memory the DMA engines can address (cudaHostAlloc'd, or registered with xGpuHostRegister) is copied
+ * directly.  PAGEABLE caller memory -- what the reference's caller allocates with _aligned_malloc,
+ * src/x266.cpp:505,647-649 -- is staged through a library-owned pinned ring by a pool of host copy threads
+ * (all batch entry points, the intra entry points and the search outputs; the few call-wide inputs -- search
+ * planes, tiled frames, the Tier-2 single calls -- are handed to cudaMemcpyAsync, which stages them itself).
+ * Each call leases its own streams, so host threads sharing a GPU overlap.  *Dev forms take device pointers on
+ * the current device plus a cudaStream_t passed as void* (NULL = legacy default stream), enqueue only, and
+ * never synchronise (the first call on a device initialises it: xGpuInit does the same ahead of time).
  * ============================================================================================== */
 
 /* Mirrors xCodecInit/xCodecFree (src/x266.cpp:494-524).  device < 0 = current device.  Optional:
@@ -72,6 +77,12 @@ int satd8x8(const int16_t diff[64]);
 int  xGpuInit(int device);
 void xGpuFree(void);
 const char* xGpuLastError(void);
+/* Optional, for callers that allocate their frame buffers once (as main() does, src/x266.cpp:647-649): page-lock an
+ * existing allocation so every later host-pointer call DMAs it directly instead of staging it.  Unregister before free(). */
+int  xGpuHostRegister(void* p, size_t bytes);
+int  xGpuHostUnregister(void* p);
+/* threads (incl. the caller) that copy pageable caller memory to and from the pinned ring (xGpuTune 13 / X266_HOST_COPY_THREADS) */
+int  xGpuHostCopyThreads(void);
 /* Number of kernels this library has launched since load (for the bench's gpu_launches claim). */
 unsigned long long xGpuKernelLaunches(void);
 
@@ -86,7 +97,9 @@ int xGpuSetDctVariant(int variant);
  * key 0 IMMA DCT32 instantiation (warps, stages, CTAs/SM, staging; scripts/tune_dct.py) | 1 SATD search kernel (0 v3 packed
  * transform domain, 1 one CTA per block, 2/3 v2 strips) | 2 SATD batch variant | 3 CUDA-core DCT 8/16 | 4 blocks per chunk of the
  * host-pointer DCT pipeline | 5 CUDA-core intra decision | 6 accumulate form of the v3 search | 7 first-generation SAD search | 8 CUDA-core SWAR intra interpolation |
- * 9 / 10 / 11 CTAs per SM of the intra / DCT8 / DCT4 persistent grids (0 = shipped). */
+ * 9 / 10 / 11 CTAs per SM of the intra / DCT8 / DCT4 persistent grids (0 = shipped) | 12 pageable host buffers: 0 staged through the
+ * pinned ring (shipped), 1 handed to the driver, 2 cudaHostRegister per call | 13 host copy threads (0 = X266_HOST_COPY_THREADS or
+ * min(8, cpus/2)) | 14 non-temporal staging copies (1 = shipped) | 15 device-side mode[] range check in the *Dev intra entry points. */
 int xGpuTune(int key, int value);
 
 /* 2-D forward 32x32 transform of nBlocks contiguous row-major int16 blocks:

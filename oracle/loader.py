@@ -81,10 +81,10 @@ class Oracle:
         (self.lib.orc_partialDense if dense else self.lib.orc_partialButterfly)(src.ravel(), dst, shift, line, log2n)
         return dst
 
-    def dct(self, src, log2n=5, shift1=4, shift2=11, threads=1):
-        """src: [nBlocks, N, N] int16 -> same shape."""
+    def dct(self, src, log2n=5, shift1=4, shift2=11, threads=1, out=None):
+        """src: [nBlocks, N, N] int16 -> same shape (out: preallocated result, so a timed call pays no first-touch faults)."""
         src = np.ascontiguousarray(src, np.int16)
-        dst = np.empty_like(src)
+        dst = np.empty_like(src) if out is None else out
         n = src.size >> (2 * log2n)
         rc = self.lib.orc_dct_batch(src.ravel(), dst.ravel(), n, log2n, shift1, shift2, threads)
         assert rc == 0
@@ -207,15 +207,15 @@ class Ref:
         self.lib.ref_partialButterfly32(src.ravel(), dst, shift, line)
         return dst
 
-    def dct32(self, src, shift1=4, shift2=11, threads=1):
+    def dct32(self, src, shift1=4, shift2=11, threads=1, out=None):
         src = np.ascontiguousarray(src, np.int16)
-        dst = np.empty_like(src)
+        dst = np.empty_like(src) if out is None else out
         assert self.lib.ref_dct32_batch(src.ravel(), dst.ravel(), src.size // 1024, shift1, shift2, threads) == 0
         return dst
 
-    def satd(self, diff, threads=1):
+    def satd(self, diff, threads=1, out=None):
         diff = np.ascontiguousarray(diff, np.int16)
-        out = np.empty(diff.size // 64, np.int32)
+        out = np.empty(diff.size // 64, np.int32) if out is None else out
         assert self.lib.ref_satd8x8_batch(diff.ravel(), out, out.size, threads) == 0
         return out
 

@@ -55,3 +55,14 @@ def test_fails_loudly_without_gpu(x266):
         x266.xDct32Batch(np.zeros(1024, np.int16))
     with pytest.raises(x266.X266Error):
         x266.xSatd8x8Batch(np.zeros(64, np.int16))
+
+
+def test_host_copy_pool(tmp_path):
+    """host logic of the pageable path (no GPU): the staging copy pool is exact for every thread count / store kind, with
+    misaligned ends and concurrent callers"""
+    import subprocess
+    csrc = os.path.join(ROOT, "x266_b200", "csrc")
+    exe = str(tmp_path / "hostcopy_test")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", csrc, os.path.join(ROOT, "tests", "c", "hostcopy_test.cpp"),
+                           os.path.join(csrc, "hostcopy.cpp"), "-o", exe, "-lpthread"])
+    assert subprocess.check_output([exe], text=True, stderr=subprocess.DEVNULL).strip() == "ok"

@@ -6,7 +6,7 @@ own names (src_tb/dct32.c, src_tb/satd.c) and the batched ``x*`` entry points.  
 if the CUDA library is missing or unusable the import of ``lib()`` raises -- there is no CPU path.
 """
 from .binding import (  # noqa: F401
-    LIB_PATH, lib, build, last_error, kernel_launches, set_dct_variant, tune,
+    LIB_PATH, lib, build, last_error, kernel_launches, set_dct_variant, tune, host_register, host_unregister, host_copy_threads,
     DCT_AUTO, DCT_BFLY, DCT_IMMA,
     partialButterfly32, satd8x8, g_t32,
     xDct32Batch, xDctNBatch, xSatd8x8Batch, xSatd8x8Search, xIntra32Pred,

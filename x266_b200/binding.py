@@ -46,6 +46,8 @@ def lib():
     L.xGpuKernelLaunches.restype = C.c_ulonglong
     L.xGpuSetDctVariant.argtypes = [i]
     L.xGpuTune.argtypes = [i, i]
+    L.xGpuHostRegister.argtypes = [vp, sz]
+    L.xGpuHostUnregister.argtypes = [vp]
     L.xIntra32MmaTable.argtypes = [vp]
     L.xDct32Batch.argtypes = [vp, vp, sz, i, i]
     L.xDct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
@@ -100,6 +102,19 @@ def xIntra32MmaTable():
     t = np.zeros((35, 2, 32, 4), np.uint32)
     _ck(lib().xIntra32MmaTable(t.ctypes.data), "xIntra32MmaTable")
     return t
+
+
+def host_register(a):
+    """page-lock an existing numpy array (xGpuHostRegister); pair with host_unregister before it is freed"""
+    _ck(lib().xGpuHostRegister(a.ctypes.data, a.nbytes), "xGpuHostRegister")
+
+
+def host_copy_threads():
+    return int(lib().xGpuHostCopyThreads())
+
+
+def host_unregister(a):
+    _ck(lib().xGpuHostUnregister(a.ctypes.data), "xGpuHostUnregister")
 
 
 def tune(key, value):

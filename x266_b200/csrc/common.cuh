@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 
 #define X266_HD __host__ __device__ __forceinline__
 

@@ -330,7 +330,7 @@ dct4_xchg_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static int g_dct4Ctas = 0;       // tuning/diagnostic: CTAs per SM of dct4_xchg's persistent grid (0 = 12: measured 4/6/8/10/12/16 ->
+static std::atomic<int> g_dct4Ctas{0};       // tuning/diagnostic: CTAs per SM of dct4_xchg's persistent grid (0 = 12: measured 4/6/8/10/12/16 ->
                                  // 5829/5681/6124/6065/6357/6338 GB/s on 1 Gi samples, scripts/time_small_dct_grid.py)
 void set_dct4_ctas(int v) { g_dct4Ctas = v; }
 
@@ -358,7 +358,7 @@ cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int li
     return cudaGetLastError();
 }
 
-static int g_smallCuda = 0;     // 0: shipped (IMMA for N=8,16; lane-exchange kernel for N=4); 1: smem-staged dctN kernels; 2: N=4 one block per thread
+static std::atomic<int> g_smallCuda{0};     // 0: shipped (IMMA for N=8,16; lane-exchange kernel for N=4); 1: smem-staged dctN kernels; 2: N=4 one block per thread
 void set_small_dct_cuda_cores(int on) { g_smallCuda = on; }
 
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
@@ -367,7 +367,7 @@ cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlo
     if (log2n == 4 && g_smallCuda != 1) return launch_dct16_imma(src, dst, nBlocks, s1, s2, st);
     if (log2n == 3 && g_smallCuda != 1) return launch_dct8_imma(src, dst, nBlocks, s1, s2, st);
     if (log2n == 2 && g_smallCuda == 0) {
-        dct4_xchg_kernel<<<grid_for((nBlocks + 63) / 64, DCT4X_WARPS, g_dct4Ctas > 0 ? g_dct4Ctas : 12), DCT4X_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
+        dct4_xchg_kernel<<<grid_for((nBlocks + 63) / 64, DCT4X_WARPS, g_dct4Ctas > 0 ? g_dct4Ctas.load() : 12), DCT4X_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
         count_launch();
         return cudaGetLastError();
     }

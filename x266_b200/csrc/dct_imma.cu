@@ -413,14 +413,14 @@ dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
     }
 }
 
-static int g_dct8Ctas = 0;       // tuning/diagnostic: CTAs per SM of the persistent grid (0 = 2)
+static std::atomic<int> g_dct8Ctas{0};       // tuning/diagnostic: CTAs per SM of the persistent grid (0 = 2)
 void set_dct8_ctas(int v) { g_dct8Ctas = v; }
 
 cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
 {
     if (nBlocks == 0) return cudaSuccess;
     const size_t want = ((nBlocks + 15) / 16 + D8_WARPS - 1) / D8_WARPS;
-    const size_t cap = (size_t)sm_count() * (g_dct8Ctas > 0 ? g_dct8Ctas : 2);
+    const size_t cap = (size_t)sm_count() * (g_dct8Ctas > 0 ? g_dct8Ctas.load() : 2);
     dct8_imma_kernel<<<(int)(want < cap ? want : cap), D8_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
     count_launch();
     return cudaGetLastError();
@@ -692,14 +692,14 @@ cudaError_t launch_idct32_imma(const int16_t* src, int16_t* dst, size_t nBlocks,
 // double-buffered 128-bit global loads): 95.7 % of the measured HBM roofline on B200 vs 86.7 % for the
 // best TMA-ring instantiation (profiles/r01_tune_dct.log).
 constexpr int IMMA_DEFAULT_CFG = 6;
-static int g_immaCfg = IMMA_DEFAULT_CFG;
+static std::atomic<int> g_immaCfg{IMMA_DEFAULT_CFG};
 void set_imma_config(int id) { g_immaCfg = id < 0 ? IMMA_DEFAULT_CFG : id; }
 
 template <int W, int S, int B, bool D>
 static cudaError_t launch_cfg(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
 {
     constexpr int SMEM = D ? 0 : (W * S * 2048 + W * S * 8);
-    static bool attrSet[64] = {};
+    static std::atomic<bool> attrSet[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (SMEM > 48 * 1024 && (dev < 0 || dev >= 64 || !attrSet[dev])) {

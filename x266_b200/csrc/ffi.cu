@@ -9,8 +9,10 @@
 #include "../../include/x266_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "hostcopy.h"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,36 +46,56 @@ static int fail(const char* what, cudaError_t e)
     } while (0)
 
 constexpr int MAX_DEV = 64;
-constexpr int SLOTS = 3;
+constexpr int SLOTS = 4;            // chunks in flight per pipeline
+constexpr int LAG = 2;              // a staged chunk is copied out to the caller LAG iterations after it was enqueued (LAG < SLOTS)
+constexpr int MAX_PIPES = 4;        // concurrent host-pointer calls per device; further callers wait
+constexpr int MAX_ARR = 2;          // host arrays per direction of one call
 
-struct Ctx {
-    bool ready = false;
-    int dev = -1;
-    int sms = 0;
+// One pipeline = what ONE host-pointer call needs: SLOTS streams with their device slots, the pinned staging ring of the
+// pageable path and a buffer for call-wide inputs.  A call leases a pipeline for its duration, so two host threads on one
+// GPU run on different streams and overlap instead of serialising on a per-device lock.
+struct Pipe {
     cudaStream_t st[SLOTS] = {};
+    cudaEvent_t evIn[SLOTS] = {};      // H2D of the slot's chunk done  -> its pinned input slot may be refilled
+    cudaEvent_t evOut[SLOTS] = {};     // D2H of the slot's chunk done  -> its pinned output slot may be copied out
     void* dIn[SLOTS] = {};
     void* dOut[SLOTS] = {};
     size_t capIn[SLOTS] = {};
     size_t capOut[SLOTS] = {};
-    void* dAux = nullptr;          // persistent inputs shared by all chunks of one call (search planes)
+    void* pIn[SLOTS] = {};             // pinned staging (allocated on first pageable call only)
+    void* pOut[SLOTS] = {};
+    size_t pcapIn[SLOTS] = {};
+    size_t pcapOut[SLOTS] = {};
+    void* dAux = nullptr;              // persistent inputs shared by all chunks of one call (search planes, tiled frames)
     size_t capAux = 0;
-    std::mutex mu;                 // serialises host-pointer calls on this device
+};
+
+struct Ctx {
+    std::atomic<bool> ready{false};
+    int dev = -1;
+    int sms = 0;
+    std::mutex mu;                     // guards idle / nPipes
+    std::condition_variable cv;
+    std::vector<Pipe*> idle;
+    int nPipes = 0;
 };
 
 static Ctx g_ctx[MAX_DEV];
 static std::mutex g_initMu;
-static int g_smCache[MAX_DEV] = {};
+static std::atomic<int> g_smCache[MAX_DEV];
+static std::atomic<int> g_hostMode{0};              // xGpuTune key 12: pageable buffers 0 = staged ring, 1 = handed to the driver, 2 = cudaHostRegister per call
+static std::atomic<int> g_checkModes{0};            // xGpuTune key 15: *Dev intra entry points validate mode[] on the device (debug)
 
 int sm_count()
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 148;
-    if (!g_smCache[dev]) {
-        int n = 0;
+    int n = g_smCache[dev].load(std::memory_order_relaxed);
+    if (!n) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        g_smCache[dev] = n;
+        g_smCache[dev].store(n, std::memory_order_relaxed);
     }
-    return g_smCache[dev];
+    return n;
 }
 
 int resident_ctas_per_sm(const void* kernel, int blockThreads, size_t dynSmemBytes)
@@ -93,8 +115,31 @@ int resident_ctas_per_sm(const void* kernel, int blockThreads, size_t dynSmemByt
     return n;
 }
 
-static cudaMemPool_t g_pool[MAX_DEV] = {};
+static std::atomic<cudaMemPool_t> g_pool[MAX_DEV];
 static std::mutex g_poolMu;
+
+static cudaError_t pool_get(int dev, cudaMemPool_t* out)
+{
+    cudaMemPool_t pool = g_pool[dev].load(std::memory_order_acquire);
+    if (!pool) {
+        std::lock_guard<std::mutex> lk(g_poolMu);
+        pool = g_pool[dev].load(std::memory_order_relaxed);
+        if (!pool) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaError_t e;
+            if ((e = cudaMemPoolCreate(&pool, &props)) != cudaSuccess) return e;
+            unsigned long long keep = ~0ull;
+            if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) { cudaMemPoolDestroy(pool); return e; }
+            g_pool[dev].store(pool, std::memory_order_release);
+        }
+    }
+    *out = pool;
+    return cudaSuccess;
+}
 
 cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st)
 {
@@ -102,35 +147,27 @@ cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st)
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
-    if (!g_pool[dev]) {
-        std::lock_guard<std::mutex> lk(g_poolMu);
-        if (!g_pool[dev]) {
-            cudaMemPoolProps props = {};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.handleTypes = cudaMemHandleTypeNone;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = dev;
-            cudaMemPool_t pool;
-            if ((e = cudaMemPoolCreate(&pool, &props)) != cudaSuccess) return e;
-            unsigned long long keep = ~0ull;
-            if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
-            g_pool[dev] = pool;
-        }
-    }
-    return cudaMallocFromPoolAsync(p, bytes, g_pool[dev], st);
+    cudaMemPool_t pool;
+    if ((e = pool_get(dev, &pool)) != cudaSuccess) return e;
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
 }
 
 cudaError_t scratch_free(void* p, cudaStream_t st) { return cudaFreeAsync(p, st); }
 
+static cudaError_t kernels_device_init() { return intra_device_init(); }
+static void kernels_device_free() { intra_device_free(); }
+
+// First use of a device: everything that allocates, uploads or configures happens HERE, so that the *Dev entry points
+// really only enqueue (stream capture included): the scratch pool, the intra fragment table, the kernels' attributes.
 static int ctx_get(Ctx** out)
 {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= MAX_DEV) return fail("device index", cudaSuccess);
     Ctx& c = g_ctx[dev];
-    if (!c.ready) {
+    if (!c.ready.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lk(g_initMu);
-        if (!c.ready) {
+        if (!c.ready.load(std::memory_order_relaxed)) {
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, dev));
             if (prop.major != 10) {
@@ -139,13 +176,83 @@ static int ctx_get(Ctx** out)
             }
             c.dev = dev;
             c.sms = prop.multiProcessorCount;
-            for (int i = 0; i < SLOTS; i++) CK(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
-            c.ready = true;
+            cudaMemPool_t pool;
+            CK(pool_get(dev, &pool));
+            CK(kernels_device_init());
+            c.ready.store(true, std::memory_order_release);
         }
     }
     *out = &c;
     return 0;
 }
+
+static void pipe_destroy(Pipe* p)
+{
+    for (int i = 0; i < SLOTS; i++) {
+        if (p->st[i]) { cudaStreamSynchronize(p->st[i]); cudaStreamDestroy(p->st[i]); }
+        if (p->evIn[i]) cudaEventDestroy(p->evIn[i]);
+        if (p->evOut[i]) cudaEventDestroy(p->evOut[i]);
+        if (p->dIn[i]) cudaFree(p->dIn[i]);
+        if (p->dOut[i]) cudaFree(p->dOut[i]);
+        if (p->pIn[i]) cudaFreeHost(p->pIn[i]);
+        if (p->pOut[i]) cudaFreeHost(p->pOut[i]);
+    }
+    if (p->dAux) cudaFree(p->dAux);
+    delete p;
+}
+
+static Pipe* pipe_create()
+{
+    Pipe* p = new Pipe();
+    for (int i = 0; i < SLOTS; i++) {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->evIn[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->evOut[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {                  // nothing half-built survives
+            fail("pipeline streams/events", e);
+            pipe_destroy(p);
+            return nullptr;
+        }
+    }
+    return p;
+}
+
+// RAII lease of one pipeline of the calling thread's current device.  Releasing synchronises the pipeline's streams, so
+// no copy can still touch caller memory (or a staging slot) after the entry point has returned -- error paths included.
+struct PipeLease {
+    Ctx* c = nullptr;
+    Pipe* p = nullptr;
+    PipeLease()
+    {
+        if (ctx_get(&c)) { c = nullptr; return; }
+        std::unique_lock<std::mutex> lk(c->mu);
+        for (;;) {
+            if (!c->idle.empty()) { p = c->idle.back(); c->idle.pop_back(); return; }
+            if (c->nPipes < MAX_PIPES) { c->nPipes++; break; }
+            c->cv.wait(lk);
+        }
+        lk.unlock();
+        p = pipe_create();
+        if (!p) {
+            lk.lock();
+            c->nPipes--;
+            c->cv.notify_one();
+        }
+    }
+    ~PipeLease()
+    {
+        if (!p) return;
+        for (int s = 0; s < SLOTS; s++) cudaStreamSynchronize(p->st[s]);
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            c->idle.push_back(p);
+        }
+        c->cv.notify_one();
+    }
+    PipeLease(const PipeLease&) = delete;
+    PipeLease& operator=(const PipeLease&) = delete;
+    bool ok() const { return p != nullptr; }
+};
 
 static int ensure(void** p, size_t* cap, size_t need)
 {
@@ -157,28 +264,139 @@ static int ensure(void** p, size_t* cap, size_t need)
     return 0;
 }
 
+static int ensure_pinned(void** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*p) CK(cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    CK(cudaHostAlloc(p, need, cudaHostAllocDefault));
+    *cap = need;
+    return 0;
+}
+
+// true if the DMA engines can address [p, p+bytes) directly (cudaHostAlloc / cudaHostRegister / managed memory)
+static bool dma_addressable(const void* p, size_t bytes)
+{
+    if (!p || !bytes) return true;
+    const char* ends[2] = { (const char*)p, (const char*)p + bytes - 1 };
+    for (const char* q : ends) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost && a.type != cudaMemoryTypeManaged) return false;
+    }
+    return true;
+}
+
+// One host array of a chunked call: `unit` bytes per unit, contiguous; h == nullptr means "not wanted" (skipped).
+struct HostArr {
+    void* h;
+    size_t unit;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
 // ------------------------------------------------------------------------------------------------
-// Chunked pipeline: units are independent, so chunk i runs H2D -> kernel -> D2H on stream i%3; the
-// three streams overlap the two copy directions with compute.  Stream order makes slot reuse safe.
+// Chunked pipeline.  Units are independent, so chunk i runs H2D -> kernel -> D2H on stream i % SLOTS and the streams
+// overlap the two copy directions with compute.
+//   * caller memory the DMA engines can address (pinned / registered): copied directly, the loop only enqueues.
+//   * pageable caller memory (what the reference's caller allocates, src/x266.cpp:505,647-649): staged through the
+//     pipeline's pinned ring by the host copy pool -- in one parallel job per iteration, chunk i goes caller -> pinned
+//     input slot while chunk i-LAG (whose D2H has completed) goes pinned output slot -> caller; the DMA of the chunks in
+//     between runs underneath.  (xGpuTune 12 selects the two alternatives that were measured against it.)
+// launch(dIn[k], dOut[k], first unit, units, stream) enqueues the kernel(s) of one chunk.
 // ------------------------------------------------------------------------------------------------
 template <typename Launch>
-static int run_chunked(Ctx& c, const void* src, size_t inUnit, void* dst, size_t outUnit, size_t nUnits,
-                       size_t unitsPerChunk, Launch launch)
+static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* outs, int nOut, size_t nUnits, size_t unitsPerChunk, Launch launch)
 {
-    std::lock_guard<std::mutex> lk(c.mu);
     const size_t chunk = nUnits < unitsPerChunk ? nUnits : unitsPerChunk;
-    size_t i = 0;
-    for (size_t u0 = 0; u0 < nUnits; u0 += chunk, i++) {
+    const size_t nChunks = (nUnits + chunk - 1) / chunk;
+    const int mode = g_hostMode.load(std::memory_order_relaxed);
+
+    size_t offIn[MAX_ARR] = {}, offOut[MAX_ARR] = {}, totIn = 0, totOut = 0;
+    bool stIn[MAX_ARR] = {}, stOut[MAX_ARR] = {}, anyStIn = false, anyStOut = false;
+    std::vector<void*> registered;                           // xGpuTune(12, 2) only; unregistered after the streams have drained
+    struct Unreg {
+        std::vector<void*>& v;
+        Pipe& p;
+        ~Unreg()
+        {
+            if (v.empty()) return;
+            for (int s = 0; s < SLOTS; s++) cudaStreamSynchronize(p.st[s]);
+            for (void* q : v) cudaHostUnregister(q);
+        }
+    } unreg{ registered, p };
+    auto classify = [&](const HostArr& a) -> bool {          // true = needs staging
+        if (!a.h || dma_addressable(a.h, nUnits * a.unit) || mode == 1) return false;
+        if (mode == 2 && cudaHostRegister(a.h, nUnits * a.unit, cudaHostRegisterDefault) == cudaSuccess) { registered.push_back(a.h); return false; }
+        cudaGetLastError();
+        return true;
+    };
+    for (int k = 0; k < nIn; k++) { offIn[k] = totIn; totIn += align256(chunk * ins[k].unit); stIn[k] = classify(ins[k]); anyStIn |= stIn[k]; }
+    for (int k = 0; k < nOut; k++) { offOut[k] = totOut; if (outs[k].h) totOut += align256(chunk * outs[k].unit); stOut[k] = classify(outs[k]); anyStOut |= stOut[k]; }
+
+    const size_t nIter = nChunks + (anyStOut ? LAG : 0);
+    for (size_t i = 0; i < nIter; i++) {
         const int s = (int)(i % SLOTS);
-        const size_t nu = (nUnits - u0) < chunk ? (nUnits - u0) : chunk;
-        if (ensure(&c.dIn[s], &c.capIn[s], chunk * inUnit)) return -1;
-        if (ensure(&c.dOut[s], &c.capOut[s], chunk * outUnit)) return -1;
-        CK(cudaMemcpyAsync(c.dIn[s], (const char*)src + u0 * inUnit, nu * inUnit, cudaMemcpyHostToDevice, c.st[s]));
-        CK(launch(c.dIn[s], c.dOut[s], nu, c.st[s]));
-        CK(cudaMemcpyAsync((char*)dst + u0 * outUnit, c.dOut[s], nu * outUnit, cudaMemcpyDeviceToHost, c.st[s]));
+        const size_t u0 = i * chunk;
+        const size_t nu = i < nChunks ? ((nUnits - u0) < chunk ? (nUnits - u0) : chunk) : 0;
+        CopyJob jobs[2 * MAX_ARR];
+        int nj = 0;
+        if (anyStOut && i >= LAG) {                            // chunk j = i - LAG is back in its pinned output slot
+            const size_t j = i - LAG, uj = j * chunk, nuj = (nUnits - uj) < chunk ? (nUnits - uj) : chunk;
+            const int sj = (int)(j % SLOTS);
+            CK(cudaEventSynchronize(p.evOut[sj]));
+            for (int k = 0; k < nOut; k++)
+                if (stOut[k]) jobs[nj++] = CopyJob{ (char*)outs[k].h + uj * outs[k].unit, (char*)p.pOut[sj] + offOut[k], nuj * outs[k].unit, true };
+        }
+        if (nu) {
+            if (totIn && ensure(&p.dIn[s], &p.capIn[s], totIn)) return -1;
+            if (totOut && ensure(&p.dOut[s], &p.capOut[s], totOut)) return -1;
+            if (anyStIn) {
+                if (ensure_pinned(&p.pIn[s], &p.pcapIn[s], totIn)) return -1;
+                if (i >= SLOTS) CK(cudaEventSynchronize(p.evIn[s]));      // the slot's previous chunk has left host memory
+                for (int k = 0; k < nIn; k++)
+                    if (stIn[k]) jobs[nj++] = CopyJob{ (char*)p.pIn[s] + offIn[k], (const char*)ins[k].h + u0 * ins[k].unit, nu * ins[k].unit, false };
+            }
+            if (anyStOut && ensure_pinned(&p.pOut[s], &p.pcapOut[s], totOut)) return -1;
+        }
+        if (nj) host_copy_parallel(jobs, nj);
+        if (!nu) continue;
+        void* dI[MAX_ARR] = {};
+        void* dO[MAX_ARR] = {};
+        for (int k = 0; k < nIn; k++) {
+            dI[k] = (char*)p.dIn[s] + offIn[k];
+            const void* from = stIn[k] ? (const void*)((char*)p.pIn[s] + offIn[k]) : (const void*)((const char*)ins[k].h + u0 * ins[k].unit);
+            CK(cudaMemcpyAsync(dI[k], from, nu * ins[k].unit, cudaMemcpyHostToDevice, p.st[s]));
+        }
+        if (anyStIn) CK(cudaEventRecord(p.evIn[s], p.st[s]));
+        for (int k = 0; k < nOut; k++) dO[k] = outs[k].h ? (char*)p.dOut[s] + offOut[k] : nullptr;
+        CK(launch(dI, dO, u0, nu, p.st[s]));
+        for (int k = 0; k < nOut; k++) {
+            if (!outs[k].h) continue;
+            void* to = stOut[k] ? (void*)((char*)p.pOut[s] + offOut[k]) : (void*)((char*)outs[k].h + u0 * outs[k].unit);
+            CK(cudaMemcpyAsync(to, dO[k], nu * outs[k].unit, cudaMemcpyDeviceToHost, p.st[s]));
+        }
+        if (anyStOut) CK(cudaEventRecord(p.evOut[s], p.st[s]));
     }
-    for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(c.st[s]));
+    for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(p.st[s]));
     return 0;
+}
+
+template <typename Launch>
+static int run_chunked(const HostArr* ins, int nIn, const HostArr* outs, int nOut, size_t nUnits, size_t unitsPerChunk, Launch launch)
+{
+    PipeLease lease;
+    if (!lease.ok()) return -1;
+    return run_chunked_on(*lease.p, ins, nIn, outs, nOut, nUnits, unitsPerChunk, launch);
+}
+
+// the common case: one array in, one array out
+template <typename Launch>
+static int run_chunked(const void* src, size_t inUnit, void* dst, size_t outUnit, size_t nUnits, size_t unitsPerChunk, Launch launch)
+{
+    const HostArr in{ const_cast<void*>(src), inUnit }, out{ dst, outUnit };
+    return run_chunked(&in, 1, &out, 1, nUnits, unitsPerChunk,
+                       [&](void* const* dI, void* const* dO, size_t, size_t n, cudaStream_t st) { return launch(dI[0], dO[0], n, st); });
 }
 
 static cudaError_t dct32_dispatch(const int16_t* s, int16_t* d, size_t n, int s1, int s2, cudaStream_t st)
@@ -228,32 +446,45 @@ extern "C" int xGpuInit(int device)
 
 extern "C" void xGpuFree(void)
 {
+    // mirrors xCodecFree (src/x266.cpp:515-524): the caller has no call in flight on this device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return;
     Ctx& c = g_ctx[dev];
     std::lock_guard<std::mutex> lk(g_initMu);
+    cudaDeviceSynchronize();
     {
         std::lock_guard<std::mutex> lp(g_poolMu);
-        if (g_pool[dev]) {                       // scratch of the search kernels: caller has synchronised its streams
-            cudaDeviceSynchronize();
-            cudaMemPoolDestroy(g_pool[dev]);
-            g_pool[dev] = nullptr;
-        }
+        cudaMemPool_t pool = g_pool[dev].exchange(nullptr);
+        if (pool) cudaMemPoolDestroy(pool);        // scratch of the search kernels
     }
-    if (!c.ready) return;
-    for (int i = 0; i < SLOTS; i++) {
-        cudaStreamSynchronize(c.st[i]);
-        cudaStreamDestroy(c.st[i]);
-        if (c.dIn[i]) cudaFree(c.dIn[i]);
-        if (c.dOut[i]) cudaFree(c.dOut[i]);
-        c.dIn[i] = c.dOut[i] = nullptr; c.capIn[i] = c.capOut[i] = 0;
+    if (!c.ready.load(std::memory_order_acquire)) return;
+    {
+        std::lock_guard<std::mutex> lc(c.mu);
+        for (Pipe* p : c.idle) pipe_destroy(p);
+        c.nPipes -= (int)c.idle.size();
+        c.idle.clear();
     }
-    if (c.dAux) cudaFree(c.dAux);
-    c.dAux = nullptr; c.capAux = 0;
-    c.ready = false;
+    kernels_device_free();
+    c.ready.store(false, std::memory_order_release);
 }
 
 extern "C" const char* xGpuLastError(void) { return t_err; }
+
+extern "C" int xGpuHostRegister(void* p, size_t bytes)
+{
+    if (!p || !bytes) return fail("xGpuHostRegister", cudaSuccess);
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+extern "C" int xGpuHostCopyThreads(void) { return host_copy_threads(); }
+
+extern "C" int xGpuHostUnregister(void* p)
+{
+    if (!p) return fail("xGpuHostUnregister", cudaSuccess);
+    CK(cudaHostUnregister(p));
+    return 0;
+}
 
 extern "C" int xIntra32MmaTable(uint32_t* table)
 {
@@ -285,13 +516,26 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 10) { set_dct8_ctas(value); return 0; }
     if (key == 11) { set_dct4_ctas(value); return 0; }
     if (key == 4 && value >= 0) { g_dctChunk.store((size_t)value); return 0; }
+    if (key == 12 && value >= 0 && value <= 2) { g_hostMode.store(value); return 0; }
+    if (key == 13 && value >= 0) { set_host_copy_threads(value); return 0; }
+    if (key == 14) { set_host_copy_nt(value); return 0; }
+    if (key == 15) { g_checkModes.store(value ? 1 : 0); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
+}
+
+// *Dev entry points: the device must have been initialised (pool, tables, attributes) before they may "only enqueue";
+// the check is one atomic load after the first call.
+static int dev_ready()
+{
+    Ctx* c;
+    return ctx_get(&c);
 }
 
 extern "C" int xDct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks, int s1, int s2, void* stream)
 {
     if (!shifts_ok(s1, s2) || (nBlocks && (!dSrc || !dDst))) return fail("xDct32BatchDev", cudaSuccess);
     if ((reinterpret_cast<uintptr_t>(dSrc) | reinterpret_cast<uintptr_t>(dDst)) & 15) return fail("xDct32BatchDev: 16-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(dct32_dispatch(dSrc, dDst, nBlocks, s1, s2, (cudaStream_t)stream));
     return 0;
 }
@@ -300,14 +544,12 @@ extern "C" int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int
 {
     if (!shifts_ok(s1, s2) || (nBlocks && (!src || !dst))) return fail("xDct32Batch", cudaSuccess);
     if (nBlocks == 0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
     // 32 MiB chunks amortise the per-chunk hand-over best (47.0 GB/s each way of the 48.2 the link gives with both directions busy);
-    // below ~24 chunks the fill and drain of the three-stage pipeline cost more than that, so smaller batches use 16 Ki blocks
+    // below ~24 chunks the fill and drain of the pipeline cost more than that, so smaller batches use 16 Ki blocks
     // (profiles/r01_e2e_chunk_sweep.log).
     size_t chunk = g_dctChunk.load();
     if (chunk == 0) chunk = nBlocks >= ((size_t)3 << 18) ? 32768 : 16384;
-    return run_chunked(*c, src, 2048, dst, 2048, nBlocks, chunk,
+    return run_chunked(src, 2048, dst, 2048, nBlocks, chunk,
                        [&](void* di, void* dO, size_t n, cudaStream_t st) {
                            return dct32_dispatch((const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
                        });
@@ -345,6 +587,7 @@ extern "C" int xIdct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlock
 {
     if (!shifts_ok(s1, s2) || (nBlocks && (!dSrc || !dDst))) return fail("xIdct32BatchDev", cudaSuccess);
     if ((reinterpret_cast<uintptr_t>(dSrc) | reinterpret_cast<uintptr_t>(dDst)) & 15) return fail("xIdct32BatchDev: 16-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_idct32_imma(dSrc, dDst, nBlocks, s1, s2, (cudaStream_t)stream));
     return 0;
 }
@@ -353,9 +596,7 @@ extern "C" int xIdct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, in
 {
     if (!shifts_ok(s1, s2) || (nBlocks && (!src || !dst))) return fail("xIdct32Batch", cudaSuccess);
     if (nBlocks == 0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
-    return run_chunked(*c, src, 2048, dst, 2048, nBlocks, 8192,
+    return run_chunked(src, 2048, dst, 2048, nBlocks, 8192,
                        [&](void* di, void* dO, size_t n, cudaStream_t st) {
                            return launch_idct32_imma((const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
                        });
@@ -366,6 +607,7 @@ extern "C" int xDctNBatchDev(int log2N, const int16_t* dSrc, int16_t* dDst, size
     if (log2N == 5) return xDct32BatchDev(dSrc, dDst, nBlocks, s1, s2, stream);
     if (log2N < 2 || log2N > 5 || !shifts_ok(s1, s2) || (nBlocks && (!dSrc || !dDst))) return fail("xDctNBatchDev", cudaSuccess);
     if ((reinterpret_cast<uintptr_t>(dSrc) | reinterpret_cast<uintptr_t>(dDst)) & 15) return fail("xDctNBatchDev: 16-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_dctN(log2N, dSrc, dDst, nBlocks, s1, s2, (cudaStream_t)stream));
     return 0;
 }
@@ -375,10 +617,8 @@ extern "C" int xDctNBatch(int log2N, const int16_t* src, int16_t* dst, size_t nB
     if (log2N == 5) return xDct32Batch(src, dst, nBlocks, s1, s2);
     if (log2N < 2 || log2N > 5 || !shifts_ok(s1, s2) || (nBlocks && (!src || !dst))) return fail("xDctNBatch", cudaSuccess);
     if (nBlocks == 0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
     const size_t unit = (size_t)2 << (2 * log2N);
-    return run_chunked(*c, src, unit, dst, unit, nBlocks, (size_t)(16u << 20) / unit,
+    return run_chunked(src, unit, dst, unit, nBlocks, (size_t)(16u << 20) / unit,
                        [&](void* di, void* dO, size_t n, cudaStream_t st) {
                            return launch_dctN(log2N, (const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
                        });
@@ -387,6 +627,7 @@ extern "C" int xDctNBatch(int log2N, const int16_t* src, int16_t* dst, size_t nB
 extern "C" int xPartialButterfly32Dev(const int16_t* dSrc, int16_t* dDst, int shift, int line, void* stream)
 {
     if (shift < 1 || shift > 16 || line < 0 || (line && (!dSrc || !dDst))) return fail("xPartialButterfly32Dev", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_partial32(dSrc, dDst, shift, line, (cudaStream_t)stream));
     return 0;
 }
@@ -395,6 +636,7 @@ extern "C" int xSatd8x8BatchDev(const int16_t* dDiff, int32_t* dSatd, size_t n, 
 {
     if (n && (!dDiff || !dSatd)) return fail("xSatd8x8BatchDev", cudaSuccess);
     if (reinterpret_cast<uintptr_t>(dDiff) & 15) return fail("xSatd8x8BatchDev: 16-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_satd8x8_batch(dDiff, dSatd, n, (cudaStream_t)stream));
     return 0;
 }
@@ -403,107 +645,128 @@ extern "C" int xSatd8x8Batch(const int16_t* diff, int32_t* satd, size_t n)
 {
     if (n && (!diff || !satd)) return fail("xSatd8x8Batch", cudaSuccess);
     if (n == 0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
-    return run_chunked(*c, diff, 128, satd, 4, n, (size_t)1 << 17,
+    return run_chunked(diff, 128, satd, 4, n, (size_t)1 << 17,
                        [&](void* di, void* dO, size_t m, cudaStream_t st) {
                            return launch_satd8x8_batch((const int16_t*)di, (int32_t*)dO, m, st);
                        });
 }
 
-extern "C" int xSatd8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
-                                 size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
+typedef cudaError_t (*search_launch_t)(const uint8_t*, const uint8_t*, intptr_t, int, int, int, size_t, size_t, uint32_t*, int32_t*, cudaStream_t);
+
+static int search_dev(const char* api, search_launch_t launch, const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h,
+                      int range, size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
 {
-    if (!dCur || !dRefPadded || w <= 0 || h <= 0 || strd < w + 2 * range) return fail("xSatd8x8SearchDev", cudaSuccess);
-    CK(launch_satd8x8_search(dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, (cudaStream_t)stream));
+    if (!dCur || !dRefPadded || w <= 0 || h <= 0 || (w & 7) || (h & 7) || range < 0 || strd < w + 2 * range || blk1 < blk0 ||
+        blk1 > (size_t)(w / 8) * (h / 8))
+        return fail(api, cudaSuccess);
+    if (blk1 == blk0) return 0;
+    if (dev_ready()) return -1;
+    cudaError_t e = launch(dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(api, e);
     return 0;
 }
 
-typedef cudaError_t (*search_launch_t)(const uint8_t*, const uint8_t*, intptr_t, int, int, int, size_t, size_t, uint32_t*, int32_t*, cudaStream_t);
-static int search_host(search_launch_t launch, const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
-                       size_t blk0, size_t blk1, uint32_t* cost, int32_t* best);
+// Host form of both searches: the two planes go up once (call-wide inputs), then the block range runs through the
+// chunked pipeline with no per-chunk input and up to two outputs (cost surface, argmin triples).
+static int search_host(const char* api, search_launch_t launch, const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h,
+                       int range, size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
+{
+    if (!cur || !refPadded || w <= 0 || h <= 0 || (w & 7) || (h & 7) || range < 0 || strd < w + 2 * range || blk1 < blk0 ||
+        blk1 > (size_t)(w / 8) * (h / 8))
+        return fail(api, cudaSuccess);
+    if (blk1 == blk0) return 0;
+    const size_t curBytes = (size_t)w * h;
+    const size_t refBytes = (size_t)strd * (h + 2 * range);
+    const size_t refOff = align256(curBytes);
+    PipeLease l;
+    if (!l.ok()) return -1;
+    Pipe& p = *l.p;
+    if (ensure(&p.dAux, &p.capAux, refOff + refBytes)) return -1;
+    uint8_t* dCur = (uint8_t*)p.dAux;
+    uint8_t* dRef = dCur + refOff;
+    CK(cudaMemcpyAsync(dCur, cur, curBytes, cudaMemcpyHostToDevice, p.st[0]));
+    CK(cudaMemcpyAsync(dRef, refPadded, refBytes, cudaMemcpyHostToDevice, p.st[0]));
+    CK(cudaStreamSynchronize(p.st[0]));
+    const size_t side = (size_t)(2 * range + 1);
+    const size_t costUnit = side * side * 4;
+    // blocks per chunk: keep a chunk's cost surface around 64 MiB
+    size_t per = cost ? ((size_t)64 << 20) / costUnit : (size_t)1 << 20;
+    if (per < 1) per = 1;
+    const HostArr outs[2] = { { cost, costUnit }, { best, 12 } };
+    if (run_chunked_on(p, nullptr, 0, outs, 2, blk1 - blk0, per,
+                       [&](void* const*, void* const* dO, size_t u0, size_t nu, cudaStream_t st) {
+                           return launch(dCur, dRef, strd, w, h, range, blk0 + u0, blk0 + u0 + nu, (uint32_t*)dO[0], (int32_t*)dO[1], st);
+                       })) {
+        const std::string inner(t_err);
+        snprintf(t_err, sizeof(t_err), "%s: %s", api, inner.c_str());
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int xSatd8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                                 size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
+{
+    return search_dev("xSatd8x8SearchDev", launch_satd8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
+}
 
 extern "C" int xSatd8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
                               size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
 {
-    return search_host(launch_satd8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
+    return search_host("xSatd8x8Search", launch_satd8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
 }
 
 extern "C" int xSad8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
                              size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
 {
-    return search_host(launch_sad8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
+    return search_host("xSad8x8Search", launch_sad8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
 }
 
 extern "C" int xSad8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
                                 size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
 {
-    if (!dCur || !dRefPadded || w <= 0 || h <= 0 || strd < w + 2 * range) return fail("xSad8x8SearchDev", cudaSuccess);
-    CK(launch_sad8x8_search(dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, (cudaStream_t)stream));
-    return 0;
+    return search_dev("xSad8x8SearchDev", launch_sad8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
 }
 
 extern "C" int sad(unsigned char* input_data1, unsigned char* input_data2, size_t n)
 {
     // replaces riscv/programs/benchmarks/sad/sad.c:27-38 (host pointers, synchronous)
-    Ctx* c;
-    if (ctx_get(&c)) die("sad");
-    std::lock_guard<std::mutex> lk(c->mu);
     const size_t bytes = n * n;
     unsigned out = 0;
     auto body = [&]() -> int {
-        if (ensure(&c->dIn[0], &c->capIn[0], 2 * bytes + 256)) return -1;
-        if (ensure(&c->dOut[0], &c->capOut[0], 256)) return -1;
-        uint8_t* dA = (uint8_t*)c->dIn[0];
-        uint8_t* dB = dA + ((bytes + 255) & ~(size_t)255);
-        CK(cudaMemcpyAsync(dA, input_data1, bytes, cudaMemcpyHostToDevice, c->st[0]));
-        CK(cudaMemcpyAsync(dB, input_data2, bytes, cudaMemcpyHostToDevice, c->st[0]));
-        CK(launch_sad_region(dA, dB, bytes, (unsigned*)c->dOut[0], c->st[0]));
-        CK(cudaMemcpyAsync(&out, c->dOut[0], sizeof(out), cudaMemcpyDeviceToHost, c->st[0]));
-        CK(cudaStreamSynchronize(c->st[0]));
+        PipeLease l;
+        if (!l.ok()) return -1;
+        Pipe& p = *l.p;
+        if (ensure(&p.dIn[0], &p.capIn[0], 2 * bytes + 256)) return -1;
+        if (ensure(&p.dOut[0], &p.capOut[0], 256)) return -1;
+        uint8_t* dA = (uint8_t*)p.dIn[0];
+        uint8_t* dB = dA + align256(bytes);
+        CK(cudaMemcpyAsync(dA, input_data1, bytes, cudaMemcpyHostToDevice, p.st[0]));
+        CK(cudaMemcpyAsync(dB, input_data2, bytes, cudaMemcpyHostToDevice, p.st[0]));
+        CK(launch_sad_region(dA, dB, bytes, (unsigned*)p.dOut[0], p.st[0]));
+        CK(cudaMemcpyAsync(&out, p.dOut[0], sizeof(out), cudaMemcpyDeviceToHost, p.st[0]));
+        CK(cudaStreamSynchronize(p.st[0]));
         return 0;
     };
     if (body()) die("sad");
     return (int)out;
 }
 
-static int search_host(search_launch_t launch, const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
-                       size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
+// optional device-side validation of the mode array behind xGpuTune(15, 1): the *Dev intra entry points otherwise trust the
+// caller (the host forms always check), and an out-of-range mode is predicted as DC
+static int check_modes_dev(const char* api, const uint8_t* dMode, size_t n, cudaStream_t st)
 {
-    if (!cur || !refPadded || w <= 0 || h <= 0 || (w & 7) || (h & 7) || range < 0 || strd < w + 2 * range || blk1 < blk0 ||
-        blk1 > (size_t)(w / 8) * (h / 8))
-        return fail("xSatd8x8Search", cudaSuccess);
-    if (blk1 == blk0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
-    std::lock_guard<std::mutex> lk(c->mu);
-    const size_t curBytes = (size_t)w * h;
-    const size_t refBytes = (size_t)strd * (h + 2 * range);
-    const size_t refOff = (curBytes + 255) & ~(size_t)255;
-    if (ensure(&c->dAux, &c->capAux, refOff + refBytes)) return -1;
-    uint8_t* dCur = (uint8_t*)c->dAux;
-    uint8_t* dRef = dCur + refOff;
-    CK(cudaMemcpyAsync(dCur, cur, curBytes, cudaMemcpyHostToDevice, c->st[0]));
-    CK(cudaMemcpyAsync(dRef, refPadded, refBytes, cudaMemcpyHostToDevice, c->st[0]));
-    CK(cudaStreamSynchronize(c->st[0]));
-    const size_t side = (size_t)(2 * range + 1);
-    const size_t costUnit = cost ? side * side * 4 : 0;
-    // blocks per chunk: keep a chunk's cost surface around 64 MiB
-    size_t per = cost ? ((size_t)64 << 20) / costUnit : (size_t)1 << 20;
-    if (per < 1) per = 1;
-    size_t i = 0;
-    for (size_t b0 = blk0; b0 < blk1; b0 += per, i++) {
-        const int s = (int)(i % SLOTS);
-        const size_t nb = (blk1 - b0) < per ? (blk1 - b0) : per;
-        uint32_t* dCost = nullptr;
-        int32_t* dBest = nullptr;
-        if (cost) { if (ensure(&c->dOut[s], &c->capOut[s], per * costUnit)) return -1; dCost = (uint32_t*)c->dOut[s]; }
-        if (best) { if (ensure(&c->dIn[s], &c->capIn[s], per * 12)) return -1; dBest = (int32_t*)c->dIn[s]; }
-        CK(launch(dCur, dRef, strd, w, h, range, b0, b0 + nb, dCost, dBest, c->st[s]));
-        if (cost) CK(cudaMemcpyAsync(cost + (b0 - blk0) * side * side, dCost, nb * costUnit, cudaMemcpyDeviceToHost, c->st[s]));
-        if (best) CK(cudaMemcpyAsync(best + (b0 - blk0) * 3, dBest, nb * 12, cudaMemcpyDeviceToHost, c->st[s]));
-    }
-    for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(c->st[s]));
+    if (!g_checkModes.load(std::memory_order_relaxed) || !n) return 0;
+    unsigned* dBad = nullptr;
+    unsigned bad = 0;
+    CK(scratch_alloc((void**)&dBad, sizeof(unsigned), st));
+    CK(cudaMemsetAsync(dBad, 0, sizeof(unsigned), st));
+    cudaError_t e = launch_mode_range_check(dMode, n, 34, dBad, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, dBad, sizeof(bad), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    scratch_free(dBad, st);
+    if (e != cudaSuccess) return fail(api, e);
+    if (bad) { snprintf(t_err, sizeof(t_err), "%s: %u mode value(s) > 34", api, bad); return -1; }
     return 0;
 }
 
@@ -511,6 +774,8 @@ extern "C" int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8
 {
     if (n && (!dRefs || !dMode || !dPred)) return fail("xIntra32PredDev", cudaSuccess);
     if (reinterpret_cast<uintptr_t>(dPred) & 15) return fail("xIntra32PredDev: 16-byte alignment of pred", cudaSuccess);
+    if (dev_ready()) return -1;
+    if (check_modes_dev("xIntra32PredDev", dMode, n, (cudaStream_t)stream)) return -1;
     CK(launch_intra32(dRefs, dMode, dPred, n, (cudaStream_t)stream));
     return 0;
 }
@@ -521,32 +786,19 @@ extern "C" int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* p
     for (size_t i = 0; i < n; i++)
         if (mode[i] > 34) return fail("xIntra32Pred: mode > 34", cudaSuccess);
     if (n == 0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
-    // inputs are 129 + 1 bytes per prediction: pack refs and mode into one staged unit stream
-    std::lock_guard<std::mutex> lk(c->mu);
-    const size_t per = (size_t)1 << 15;
-    size_t i = 0;
-    for (size_t p0 = 0; p0 < n; p0 += per, i++) {
-        const int s = (int)(i % SLOTS);
-        const size_t np = (n - p0) < per ? (n - p0) : per;
-        if (ensure(&c->dIn[s], &c->capIn[s], per * 130 + 256)) return -1;
-        if (ensure(&c->dOut[s], &c->capOut[s], per * 1024)) return -1;
-        uint8_t* dRefs = (uint8_t*)c->dIn[s];
-        uint8_t* dMode = dRefs + ((per * 129 + 255) & ~(size_t)255);
-        CK(cudaMemcpyAsync(dRefs, refs + p0 * 129, np * 129, cudaMemcpyHostToDevice, c->st[s]));
-        CK(cudaMemcpyAsync(dMode, mode + p0, np, cudaMemcpyHostToDevice, c->st[s]));
-        CK(launch_intra32(dRefs, dMode, (uint8_t*)c->dOut[s], np, c->st[s]));
-        CK(cudaMemcpyAsync(pred + p0 * 1024, c->dOut[s], np * 1024, cudaMemcpyDeviceToHost, c->st[s]));
-    }
-    for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(c->st[s]));
-    return 0;
+    const HostArr ins[2] = { { const_cast<uint8_t*>(refs), 129 }, { const_cast<uint8_t*>(mode), 1 } };
+    const HostArr out{ pred, 1024 };
+    return run_chunked(ins, 2, &out, 1, n, (size_t)1 << 15,
+                       [&](void* const* dI, void* const* dO, size_t, size_t np, cudaStream_t st) {
+                           return launch_intra32((const uint8_t*)dI[0], (const uint8_t*)dI[1], (uint8_t*)dO[0], np, st);
+                       });
 }
 
 extern "C" int xTranspose32x32BatchDev(const uint8_t* dSrc, uint8_t* dDst, size_t nTiles, void* stream)
 {
     if (nTiles && (!dSrc || !dDst)) return fail("xTranspose32x32BatchDev", cudaSuccess);
     if ((reinterpret_cast<uintptr_t>(dSrc) | reinterpret_cast<uintptr_t>(dDst)) & 15) return fail("xTranspose32x32BatchDev: 16-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_transpose32(dSrc, dDst, nTiles, (cudaStream_t)stream));
     return 0;
 }
@@ -555,9 +807,7 @@ extern "C" int xTranspose32x32Batch(const uint8_t* src, uint8_t* dst, size_t nTi
 {
     if (nTiles && (!src || !dst)) return fail("xTranspose32x32Batch", cudaSuccess);
     if (nTiles == 0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
-    return run_chunked(*c, src, 1024, dst, 1024, nTiles, 16384,
+    return run_chunked(src, 1024, dst, 1024, nTiles, 16384,
                        [&](void* di, void* dO, size_t n, cudaStream_t st) { return launch_transpose32((const uint8_t*)di, (uint8_t*)dO, n, st); });
 }
 
@@ -565,6 +815,7 @@ extern "C" int xIntra32DecideDev(const uint8_t* dCur, const uint8_t* dRefs, uint
 {
     if (n && (!dCur || !dRefs || !dCost || !dBestMode)) return fail("xIntra32DecideDev", cudaSuccess);
     if (reinterpret_cast<uintptr_t>(dCur) & 3) return fail("xIntra32DecideDev: 4-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_intra32_decide(dCur, dRefs, dCost, dBestMode, n, (cudaStream_t)stream));
     return 0;
 }
@@ -573,29 +824,12 @@ extern "C" int xIntra32Decide(const uint8_t* cur, const uint8_t* refs, uint32_t*
 {
     if (n && (!cur || !refs || !cost || !bestMode)) return fail("xIntra32Decide", cudaSuccess);
     if (n == 0) return 0;
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
-    std::lock_guard<std::mutex> lk(c->mu);
-    const size_t per = (size_t)1 << 14;
-    size_t i = 0;
-    for (size_t p0 = 0; p0 < n; p0 += per, i++) {
-        const int s = (int)(i % SLOTS);
-        const size_t np = (n - p0) < per ? (n - p0) : per;
-        const size_t refOff = per * 1024, costOff = 0, bestOff = (per * 35 * 4 + 255) & ~(size_t)255;
-        if (ensure(&c->dIn[s], &c->capIn[s], per * 1024 + per * 129 + 256)) return -1;
-        if (ensure(&c->dOut[s], &c->capOut[s], bestOff + per * 4)) return -1;
-        uint8_t* dCur = (uint8_t*)c->dIn[s];
-        uint8_t* dRefs = dCur + refOff;
-        uint32_t* dCost = (uint32_t*)((uint8_t*)c->dOut[s] + costOff);
-        int32_t* dBest = (int32_t*)((uint8_t*)c->dOut[s] + bestOff);
-        CK(cudaMemcpyAsync(dCur, cur + p0 * 1024, np * 1024, cudaMemcpyHostToDevice, c->st[s]));
-        CK(cudaMemcpyAsync(dRefs, refs + p0 * 129, np * 129, cudaMemcpyHostToDevice, c->st[s]));
-        CK(launch_intra32_decide(dCur, dRefs, dCost, dBest, np, c->st[s]));
-        CK(cudaMemcpyAsync(cost + p0 * 35, dCost, np * 35 * 4, cudaMemcpyDeviceToHost, c->st[s]));
-        CK(cudaMemcpyAsync(bestMode + p0, dBest, np * 4, cudaMemcpyDeviceToHost, c->st[s]));
-    }
-    for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(c->st[s]));
-    return 0;
+    const HostArr ins[2] = { { const_cast<uint8_t*>(cur), 1024 }, { const_cast<uint8_t*>(refs), 129 } };
+    const HostArr outs[2] = { { cost, 35 * 4 }, { bestMode, 4 } };
+    return run_chunked(ins, 2, outs, 2, n, (size_t)1 << 14,
+                       [&](void* const* dI, void* const* dO, size_t, size_t np, cudaStream_t st) {
+                           return launch_intra32_decide((const uint8_t*)dI[0], (const uint8_t*)dI[1], (uint32_t*)dO[0], (int32_t*)dO[1], np, st);
+                       });
 }
 
 // ---- "next" rows: the encoder's tiled frame format on the device ---------------------------------------
@@ -604,6 +838,7 @@ extern "C" int xConvInputFmtDev(void* dTiles, const uint8_t* dY, const uint8_t* 
 {
     // replaces src/x266.cpp:415-453 on device-resident planes
     if (!dTiles || !dY || !dU || !dV || strdY < width || (reinterpret_cast<uintptr_t>(dTiles) & 15)) return fail("xConvInputFmtDev", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_conv_input_fmt((uint8_t*)dTiles, dY, dU, dV, strdY, width, height, (cudaStream_t)stream));
     return 0;
 }
@@ -614,6 +849,7 @@ extern "C" int xConvOutput420Dev(const void* dTiles, uint8_t* dY, intptr_t strdY
     // replaces src/x266.cpp:455-492
     if (!dTiles || !dY || !dU || !dV || strdY < width || strdC < width / 2 || (reinterpret_cast<uintptr_t>(dTiles) & 15))
         return fail("xConvOutput420Dev", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_conv_output420((const uint8_t*)dTiles, dY, strdY, dU, dV, strdC, width, height, (cudaStream_t)stream));
     return 0;
 }
@@ -624,6 +860,7 @@ extern "C" int xFrameResiDct32Dev(const void* dCurTiles, const void* dPredTiles,
     if (!dCurTiles || !dPredTiles || !dCoef || !shifts_ok(s1, s2)) return fail("xFrameResiDct32Dev", cudaSuccess);
     if ((reinterpret_cast<uintptr_t>(dCurTiles) | reinterpret_cast<uintptr_t>(dPredTiles) | reinterpret_cast<uintptr_t>(dCoef)) & 15)
         return fail("xFrameResiDct32Dev: 16-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
     CK(launch_frame_resi_dct32((const uint8_t*)dCurTiles, (const uint8_t*)dPredTiles, width, height, dCoef, s1, s2, (cudaStream_t)stream));
     return 0;
 }
@@ -632,20 +869,20 @@ extern "C" int xFrameResiDct32(const void* curTiles, const void* predTiles, int 
 {
     if (!curTiles || !predTiles || !coef || !shifts_ok(s1, s2) || width <= 0 || height <= 0 || (width & 31) || (height & 31))
         return fail("xFrameResiDct32", cudaSuccess);
-    Ctx* c;
-    if (ctx_get(&c)) return -1;
-    std::lock_guard<std::mutex> lk(c->mu);
+    PipeLease l;
+    if (!l.ok()) return -1;
+    Pipe& p = *l.p;
     const size_t tileBytes = (size_t)(width / 16) * (height / 16) * 512;
     const size_t coefBytes = (size_t)width * height * 2;
-    if (ensure(&c->dAux, &c->capAux, 2 * tileBytes)) return -1;
-    if (ensure(&c->dOut[0], &c->capOut[0], coefBytes)) return -1;
-    uint8_t* dCur = (uint8_t*)c->dAux;
+    if (ensure(&p.dAux, &p.capAux, 2 * tileBytes)) return -1;
+    if (ensure(&p.dOut[0], &p.capOut[0], coefBytes)) return -1;
+    uint8_t* dCur = (uint8_t*)p.dAux;
     uint8_t* dPred = dCur + tileBytes;
-    CK(cudaMemcpyAsync(dCur, curTiles, tileBytes, cudaMemcpyHostToDevice, c->st[0]));
-    CK(cudaMemcpyAsync(dPred, predTiles, tileBytes, cudaMemcpyHostToDevice, c->st[0]));
-    CK(launch_frame_resi_dct32(dCur, dPred, width, height, (int16_t*)c->dOut[0], s1, s2, c->st[0]));
-    CK(cudaMemcpyAsync(coef, c->dOut[0], coefBytes, cudaMemcpyDeviceToHost, c->st[0]));
-    CK(cudaStreamSynchronize(c->st[0]));
+    CK(cudaMemcpyAsync(dCur, curTiles, tileBytes, cudaMemcpyHostToDevice, p.st[0]));
+    CK(cudaMemcpyAsync(dPred, predTiles, tileBytes, cudaMemcpyHostToDevice, p.st[0]));
+    CK(launch_frame_resi_dct32(dCur, dPred, width, height, (int16_t*)p.dOut[0], s1, s2, p.st[0]));
+    CK(cudaMemcpyAsync(coef, p.dOut[0], coefBytes, cudaMemcpyDeviceToHost, p.st[0]));
+    CK(cudaStreamSynchronize(p.st[0]));
     return 0;
 }
 
@@ -656,17 +893,17 @@ extern "C" void partialButterfly32(const int16_t* src, int16_t* dst, int shift, 
 {
     // replaces src_tb/dct32.c:66-170
     if (line <= 0) return;
-    Ctx* c;
-    if (ctx_get(&c)) die("partialButterfly32");
-    std::lock_guard<std::mutex> lk(c->mu);
     const size_t bytes = (size_t)line * 64;
     auto body = [&]() -> int {
-        if (ensure(&c->dIn[0], &c->capIn[0], bytes)) return -1;
-        if (ensure(&c->dOut[0], &c->capOut[0], bytes)) return -1;
-        CK(cudaMemcpyAsync(c->dIn[0], src, bytes, cudaMemcpyHostToDevice, c->st[0]));
-        CK(launch_partial32((const int16_t*)c->dIn[0], (int16_t*)c->dOut[0], shift, line, c->st[0]));
-        CK(cudaMemcpyAsync(dst, c->dOut[0], bytes, cudaMemcpyDeviceToHost, c->st[0]));
-        CK(cudaStreamSynchronize(c->st[0]));
+        PipeLease l;
+        if (!l.ok()) return -1;
+        Pipe& p = *l.p;
+        if (ensure(&p.dIn[0], &p.capIn[0], bytes)) return -1;
+        if (ensure(&p.dOut[0], &p.capOut[0], bytes)) return -1;
+        CK(cudaMemcpyAsync(p.dIn[0], src, bytes, cudaMemcpyHostToDevice, p.st[0]));
+        CK(launch_partial32((const int16_t*)p.dIn[0], (int16_t*)p.dOut[0], shift, line, p.st[0]));
+        CK(cudaMemcpyAsync(dst, p.dOut[0], bytes, cudaMemcpyDeviceToHost, p.st[0]));
+        CK(cudaStreamSynchronize(p.st[0]));
         return 0;
     };
     if (shift < 1 || shift > 16) { fail("partialButterfly32: shift", cudaSuccess); die("partialButterfly32"); }

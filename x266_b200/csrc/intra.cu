@@ -93,23 +93,61 @@ void intra_mma_table_copy(uint32_t* out)
     for (size_t i = 0; i < h.size(); i++) out[i] = h[i];
 }
 
+// Per-device copy of the table.  Uploaded by intra_device_init() when the library first touches a device (ffi.cu: ctx_get), so the
+// launchers below only enqueue; released by intra_device_free() (xGpuFree).
+static std::atomic<const uint32_t*> g_dTab[64];
+static std::mutex g_dTabMu;
+
+cudaError_t intra_device_init()
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(g_dTabMu);
+    if (g_dTab[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+    const std::vector<uint32_t> h = intra_mma_table_host();
+    uint32_t* d = nullptr;
+    if ((e = cudaMalloc((void**)&d, h.size() * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return e; }
+    g_dTab[dev].store(d, std::memory_order_release);
+    return cudaSuccess;
+}
+
+void intra_device_free()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(g_dTabMu);
+    const uint32_t* d = g_dTab[dev].exchange(nullptr);
+    if (d) cudaFree(const_cast<uint32_t*>(d));
+}
+
+__global__ void mode_range_check_kernel(const uint8_t* __restrict__ mode, size_t n, int maxMode, unsigned* __restrict__ bad)
+{
+    unsigned c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += mode[i] > maxMode;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(bad, c);
+}
+
+cudaError_t launch_mode_range_check(const uint8_t* mode, size_t n, int maxMode, unsigned* bad, cudaStream_t st)
+{
+    const size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 8;
+    mode_range_check_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(mode, n, maxMode, bad);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static const uint32_t* intra_mma_table_dev(cudaError_t* err)
 {
-    static const uint32_t* dTab[64] = {};
-    static std::mutex mu;
     int dev = 0;
     *err = cudaGetDevice(&dev);
     if (*err != cudaSuccess) return nullptr;
     if (dev < 0 || dev >= 64) { *err = cudaErrorInvalidDevice; return nullptr; }
-    std::lock_guard<std::mutex> lk(mu);
-    if (!dTab[dev]) {
-        const std::vector<uint32_t> h = intra_mma_table_host();
-        uint32_t* d = nullptr;
-        if ((*err = cudaMalloc((void**)&d, h.size() * sizeof(uint32_t))) != cudaSuccess) return nullptr;
-        if ((*err = cudaMemcpy(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return nullptr; }
-        dTab[dev] = d;
-    }
-    return dTab[dev];
+    const uint32_t* d = g_dTab[dev].load(std::memory_order_acquire);
+    if (!d) *err = cudaErrorInitializationError;       // the C ABI initialises the device before any launch (ffi.cu: dev_ready)
+    return d;
 }
 
 // One warp per prediction.  Lane l produces, for it = 0..7, the 4 pixels (row 4*it + (l>>3), columns
@@ -679,7 +717,7 @@ intra32_decide_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     }
 }
 
-static int g_decideV1 = 0;
+static std::atomic<int> g_decideV1{0};
 void set_decide_v1(int on) { g_decideV1 = on; }
 
 cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st)
@@ -693,9 +731,9 @@ cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint3
     return cudaGetLastError();
 }
 
-static int g_intraCtas = 0;      // tuning/diagnostic: CTAs per SM of the persistent grid (0 = 8)
+static std::atomic<int> g_intraCtas{0};      // tuning/diagnostic: CTAs per SM of the persistent grid (0 = 8)
 void set_intra_ctas(int v) { g_intraCtas = v; }
-static int g_intraSwar = 0;      // tuning/diagnostic: 1 = CUDA-core SWAR interpolation for every angular mode
+static std::atomic<int> g_intraSwar{0};      // tuning/diagnostic: 1 = CUDA-core SWAR interpolation for every angular mode
 void set_intra_swar(int on) { g_intraSwar = on; }
 
 cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st)
@@ -704,7 +742,7 @@ cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pr
     if (n > ((size_t)1 << 31)) return cudaErrorInvalidValue;          // 32-bit prediction index in the kernel (2 TiB of output)
     const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
     const bool aligned4 = (reinterpret_cast<uintptr_t>(refs) & 3) == 0;
-    const int perSm = g_intraCtas > 0 ? g_intraCtas
+    const int perSm = g_intraCtas > 0 ? g_intraCtas.load()
                                       : resident_ctas_per_sm(aligned4 ? (const void*)intra32_kernel<true> : (const void*)intra32_kernel<false>, INTRA_WARPS * 32, 0);
     const size_t cap = (size_t)sm_count() * perSm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);

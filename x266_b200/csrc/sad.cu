@@ -234,7 +234,7 @@ static cudaError_t launch_sad_v2(const uint8_t* cur, const uint8_t* refPad, intp
     return srch_launch<R>(sad8x8_search_v2_kernel<R>, srch_attr_flag<Tag>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
 }
 
-static int g_sadSearchV1 = 0;
+static std::atomic<int> g_sadSearchV1{0};
 void set_sad_search_v1(int on) { g_sadSearchV1 = on; }
 
 cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, unsigned* out, cudaStream_t st)

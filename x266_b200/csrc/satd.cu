@@ -508,7 +508,7 @@ satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     }
 }
 
-static int g_searchV1 = 0;      // 0: v3 (satd_search3.cu); 1: v1; 2: v2 squeezed to 3 CTAs/SM; 3: v2, 2 CTAs/SM
+static std::atomic<int> g_searchV1{0};      // 0: v3 (satd_search3.cu); 1: v1; 2: v2 squeezed to 3 CTAs/SM; 3: v2, 2 CTAs/SM
 void set_search_v1(int on) { g_searchV1 = on; }
 
 template <int R>
@@ -739,7 +739,7 @@ satd8x8_imma3_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out
     }
 }
 
-static int g_satdCuda = 0;      // tuning/diagnostic: 0 = IMMA v2 fed by a 3-stage cp.async ring (shipped), 1 = CUDA-core kernel, 2 = IMMA v1 (32 IMMA per unit),
+static std::atomic<int> g_satdCuda{0};      // tuning/diagnostic: 0 = IMMA v2 fed by a 3-stage cp.async ring (shipped), 1 = CUDA-core kernel, 2 = IMMA v1 (32 IMMA per unit),
                                 // 3 = IMMA v2 register double-buffered at 3 CTAs/SM, 4 = the same at 2 CTAs/SM, 5 = ring with 4 stages
 void set_satd_cuda_cores(int on) { g_satdCuda = on; }
 
@@ -752,7 +752,7 @@ cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cu
         const int grid = (int)(want < cap ? want : cap);
         if (g_satdCuda == 0 || g_satdCuda == 5) {                 // shipped: cp.async ring, 3 stages (5: 4 stages)
             constexpr int smem3 = SATDI_WARPS * 3 * 2048, smem4 = SATDI_WARPS * 4 * 2048;
-            static bool attrSet4[64] = {};
+            static std::atomic<bool> attrSet4[64];
             int dev = 0;
             cudaGetDevice(&dev);
             if (g_satdCuda == 5 && (dev < 0 || dev >= 64 || !attrSet4[dev])) {
@@ -769,7 +769,7 @@ cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cu
         count_launch();
         return cudaGetLastError();
     }
-    static bool attrSet[64] = {};
+    static std::atomic<bool> attrSet[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attrSet[dev]) {

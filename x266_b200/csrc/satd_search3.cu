@@ -209,7 +209,7 @@ __global__ void srch_keys_decode_kernel(const unsigned long long* __restrict__ k
     best[3 * b + 2] = (int)((k >> 12) & 0xFFF) - R;
 }
 
-static int g_accForm = 1;
+static std::atomic<int> g_accForm{1};
 void set_search_acc_form(int f) { g_accForm = f; }
 
 template <int R, int ACCF>

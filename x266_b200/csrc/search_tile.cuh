@@ -53,7 +53,7 @@ __global__ void srch_keys_decode_kernel(const unsigned long long* __restrict__ k
 // Launches `kern` (signature of both search kernels) over the units that cover blocks [blk0, blk1), with the stream-ordered key scratch
 // and the decode kernel when the argmin is wanted.
 template <int R, typename Kern>
-static cudaError_t srch_launch(Kern kern, bool& attrSet, const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
+static cudaError_t srch_launch(Kern kern, std::atomic<bool>& attrSet, const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
                                uint32_t* cost, int32_t* best, cudaStream_t st)
 {
     const int bw = w / 8;
@@ -67,27 +67,31 @@ static cudaError_t srch_launch(Kern kern, bool& attrSet, const uint8_t* cur, con
     }
     const size_t nb = blk1 - blk0;
     unsigned long long* keys = nullptr;
-    if (best) {
-        if ((e = scratch_alloc((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(keys, 0xFF, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+    if (best && (e = scratch_alloc((void**)&keys, nb * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+    // from here on every exit path hands the key scratch back to the pool
+    if (best) e = cudaMemsetAsync(keys, 0xFF, nb * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) {
+        kern<<<grid, 32, 0, st>>>(cur, refPad, strd, w, y0, blk0, blk1, cost, keys);
+        count_launch();
+        e = cudaGetLastError();
     }
-    kern<<<grid, 32, 0, st>>>(cur, refPad, strd, w, y0, blk0, blk1, cost, keys);
-    count_launch();
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (best) {
+    if (e == cudaSuccess && best) {
         srch_keys_decode_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(keys, best, nb, R);
         count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = scratch_free(keys, st)) != cudaSuccess) return e;
+        e = cudaGetLastError();
     }
-    return cudaSuccess;
+    if (keys) {
+        const cudaError_t ef = scratch_free(keys, st);
+        if (e == cudaSuccess) e = ef;
+    }
+    return e;
 }
 
 // per-device "attribute already set" flag of one kernel instantiation
 template <typename Tag>
-static bool& srch_attr_flag()
+static std::atomic<bool>& srch_attr_flag()
 {
-    static bool flags[65] = {};                      // [64] = devices beyond the table: always re-set
+    static std::atomic<bool> flags[65];              // [64] = devices beyond the table: always re-set
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) { flags[64] = false; return flags[64]; }
