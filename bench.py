@@ -356,7 +356,7 @@ class Env:
     def pinned(self, shape, dtype):
         return self.torch.empty(shape, dtype=dtype, pin_memory=True)
 
-    def link_ceiling(self, mb=512, reps=4):
+    def link_ceiling(self, mb=512, reps=8, rounds=3):
         """GB/s each way, summed over ranks: concurrent pure H2D + D2H copies from pinned memory, every rank at the same time --
         what the host link gives a host-buffer call that moves as many bytes out as in (scripts/time_link_ceiling.py)"""
         torch = self.torch
@@ -374,14 +374,18 @@ class Env:
                 hout.copy_(dout, non_blocking=True)
 
         go()
+        go()
+        best = None
+        for _ in range(rounds):                              # best of `rounds`: a ceiling must not be undercut by a cold first pass
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                go()
+            torch.cuda.synchronize()
+            dt = self.max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
         self.barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            go()
-        torch.cuda.synchronize()
-        dt = self.max_over_ranks(time.perf_counter() - t0)
-        self.barrier()
-        return self.world * n * reps / dt / 1e9
+        return self.world * n * reps / best / 1e9
 
     def hbm_entry(self, metric, units, bytes_per_unit, ms, note=None):
         gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9            # per GPU
@@ -586,6 +590,26 @@ def e2e_dct32(env, src, dst):
     out["pageable"] = {"value": pv, "unit": "blocks/s", "frac_of_pinned": pv / value, "matches_device_path": bool(np.array_equal(pb, b.reshape(-1)[:pn * 1024])),
                        "api": "xDct32Batch (host pointers, posix_memalign-style pageable buffers, staged ring)",
                        "host_copy_threads_per_rank": int(xb.host_copy_threads()), "sample": f"{pf} frames per step per rank, 3 steps"}
+    # the same pageable buffers page-locked once with xGpuHostRegister -- what a caller that allocates its frame buffers once
+    # (src/x266.cpp:647-649) does at start-up; registration time is reported, not inside the timed region
+    try:
+        t0 = time.perf_counter()
+        xb.host_register(pa)
+        xb.host_register(pb)
+        reg_ms = (time.perf_counter() - t0) * 1e3
+        try:
+            pb[:] = 0
+            sec = env.wall(lambda: xb.xDct32Batch(pa, *SHIFTS, out=pb), 3, warm=1)
+            rv = world * pn / sec
+            out["registered"] = {"value": rv, "unit": "blocks/s", "frac_of_pinned": rv / value,
+                                 "matches_device_path": bool(np.array_equal(pb, b.reshape(-1)[:pn * 1024])),
+                                 "api": "xGpuHostRegister once, then xDct32Batch on the same malloc'd buffers",
+                                 "register_ms_once": reg_ms, "registered_bytes": int(2 * pn * 2048)}
+        finally:
+            xb.host_unregister(pa)
+            xb.host_unregister(pb)
+    except Exception as e:
+        out["registered"] = {"value": None, "error": str(e)[:200]}
     del pa, pb
     if world > 1:
         # the native single-process form: ONE process, one host thread per GPU (xDct32BatchMultiGpu), the other ranks idle
@@ -593,7 +617,7 @@ def e2e_dct32(env, src, dst):
         env.host_barrier()
         if env.rank == 0:
             try:
-                per = max(4, frames // 2)
+                per = max(4, frames // 4)
                 tot = world * per * BLOCKS_PER_FRAME
                 big_in = env.pinned((tot, 32, 32), torch.int16)
                 big_out = env.pinned((tot, 32, 32), torch.int16)

@@ -48,7 +48,7 @@ def topo():
     return info
 
 
-def measure(devs, mb, reps, direction):
+def measure(devs, mb, reps, direction, seconds_out=None):
     """direction: 'h2d', 'd2h' or 'both'; returns GB/s each way, total over devs (wall clock around a full sync)."""
     n = mb << 20
     bufs = []
@@ -77,6 +77,8 @@ def measure(devs, mb, reps, direction):
     t = time.perf_counter()
     go(reps)
     dt = time.perf_counter() - t
+    if seconds_out is not None:
+        seconds_out.append(dt)
     return len(devs) * n * reps / dt / 1e9
 
 
@@ -95,15 +97,22 @@ def main():
         for direction in ("h2d", "d2h", "both"):
             dist.barrier()
             torch.cuda.synchronize()
-            v = measure([local], args.mb, args.reps, direction)
+            secs = []
+            v = measure([local], args.mb, args.reps, direction, secs)
             t = torch.tensor([v], dtype=torch.float64, device="cuda")
             mn = t.clone()
+            mx = torch.tensor([secs[0]], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             if rank == 0:
+                # equal work per rank finishes with the slowest rank: `equal_split` is what a statically sharded job can get;
+                # `sum_of_rank_rates` (each rank over its own duration) is what a dynamically balanced one could approach
+                eq = world * (args.mb << 20) * args.reps / float(mx.item()) / 1e9
                 print(json.dumps({"form": "one process per GPU", "gpus": world, "direction": direction,
-                                  "each_way_GBps_total": float(t.item()), "slowest_rank_GBps": float(mn.item()),
-                                  "e2e_blocks_per_s_ceiling": float(t.item()) * 1e9 / 2048 if direction == "both" else None}), flush=True)
+                                  "each_way_GBps_total_equal_split": eq, "sum_of_rank_rates_GBps": float(t.item()),
+                                  "slowest_rank_GBps": float(mn.item()),
+                                  "e2e_blocks_per_s_ceiling": eq * 1e9 / 2048 if direction == "both" else None}), flush=True)
         dist.destroy_process_group()
         return
     print(json.dumps({"topology": topo()}), flush=True)

@@ -305,11 +305,27 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 //     between runs underneath.  (xGpuTune 12 selects the two alternatives that were measured against it.)
 // launch(dIn[k], dOut[k], first unit, units, stream) enqueues the kernel(s) of one chunk.
 // ------------------------------------------------------------------------------------------------
+// Where the next chunk of a call comes from.  A single-GPU call walks its range in order; the multi-GPU entry point shares ONE
+// claimer between its per-device threads, so a GPU with a slower host link simply claims fewer chunks (the links of one box are
+// not equal: profiles/r02_link_ceiling.md).
+struct ChunkClaimer {
+    std::atomic<size_t> next{0};
+    size_t nUnits = 0, chunk = 0;
+    ChunkClaimer(size_t n, size_t c) : nUnits(n), chunk(c) {}
+    bool claim(size_t* u0, size_t* nu)
+    {
+        const size_t at = next.fetch_add(chunk, std::memory_order_relaxed);
+        if (at >= nUnits) return false;
+        *u0 = at;
+        *nu = (nUnits - at) < chunk ? (nUnits - at) : chunk;
+        return true;
+    }
+};
+
 template <typename Launch>
-static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* outs, int nOut, size_t nUnits, size_t unitsPerChunk, Launch launch)
+static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* outs, int nOut, ChunkClaimer& claimer, Launch launch)
 {
-    const size_t chunk = nUnits < unitsPerChunk ? nUnits : unitsPerChunk;
-    const size_t nChunks = (nUnits + chunk - 1) / chunk;
+    const size_t nUnits = claimer.nUnits, chunk = claimer.chunk;
     const int mode = g_hostMode.load(std::memory_order_relaxed);
 
     size_t offIn[MAX_ARR] = {}, offOut[MAX_ARR] = {}, totIn = 0, totOut = 0;
@@ -334,21 +350,25 @@ static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* o
     for (int k = 0; k < nIn; k++) { offIn[k] = totIn; totIn += align256(chunk * ins[k].unit); stIn[k] = classify(ins[k]); anyStIn |= stIn[k]; }
     for (int k = 0; k < nOut; k++) { offOut[k] = totOut; if (outs[k].h) totOut += align256(chunk * outs[k].unit); stOut[k] = classify(outs[k]); anyStOut |= stOut[k]; }
 
-    const size_t nIter = nChunks + (anyStOut ? LAG : 0);
-    for (size_t i = 0; i < nIter; i++) {
+    struct Fly { size_t u0, nu; int s; };
+    Fly fly[SLOTS];                                          // staged chunks enqueued but not yet copied out to the caller, oldest first
+    int nFly = 0;
+    for (size_t i = 0;; ) {
+        size_t u0 = 0, nu = 0;
+        const bool got = claimer.claim(&u0, &nu);
+        if (!got && nFly == 0) break;
         const int s = (int)(i % SLOTS);
-        const size_t u0 = i * chunk;
-        const size_t nu = i < nChunks ? ((nUnits - u0) < chunk ? (nUnits - u0) : chunk) : 0;
         CopyJob jobs[2 * MAX_ARR];
         int nj = 0;
-        if (anyStOut && i >= LAG) {                            // chunk j = i - LAG is back in its pinned output slot
-            const size_t j = i - LAG, uj = j * chunk, nuj = (nUnits - uj) < chunk ? (nUnits - uj) : chunk;
-            const int sj = (int)(j % SLOTS);
-            CK(cudaEventSynchronize(p.evOut[sj]));
+        if (nFly && (nFly >= LAG || !got)) {                  // the oldest staged chunk is back in its pinned output slot (or will be: wait for it)
+            const Fly f = fly[0];
+            for (int q = 1; q < nFly; q++) fly[q - 1] = fly[q];
+            nFly--;
+            CK(cudaEventSynchronize(p.evOut[f.s]));
             for (int k = 0; k < nOut; k++)
-                if (stOut[k]) jobs[nj++] = CopyJob{ (char*)outs[k].h + uj * outs[k].unit, (char*)p.pOut[sj] + offOut[k], nuj * outs[k].unit, true };
+                if (stOut[k]) jobs[nj++] = CopyJob{ (char*)outs[k].h + f.u0 * outs[k].unit, (char*)p.pOut[f.s] + offOut[k], f.nu * outs[k].unit, true };
         }
-        if (nu) {
+        if (got) {
             if (totIn && ensure(&p.dIn[s], &p.capIn[s], totIn)) return -1;
             if (totOut && ensure(&p.dOut[s], &p.capOut[s], totOut)) return -1;
             if (anyStIn) {
@@ -360,7 +380,7 @@ static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* o
             if (anyStOut && ensure_pinned(&p.pOut[s], &p.pcapOut[s], totOut)) return -1;
         }
         if (nj) host_copy_parallel(jobs, nj);
-        if (!nu) continue;
+        if (!got) continue;
         void* dI[MAX_ARR] = {};
         void* dO[MAX_ARR] = {};
         for (int k = 0; k < nIn; k++) {
@@ -376,10 +396,21 @@ static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* o
             void* to = stOut[k] ? (void*)((char*)p.pOut[s] + offOut[k]) : (void*)((char*)outs[k].h + u0 * outs[k].unit);
             CK(cudaMemcpyAsync(to, dO[k], nu * outs[k].unit, cudaMemcpyDeviceToHost, p.st[s]));
         }
-        if (anyStOut) CK(cudaEventRecord(p.evOut[s], p.st[s]));
+        if (anyStOut) {
+            CK(cudaEventRecord(p.evOut[s], p.st[s]));
+            fly[nFly++] = Fly{ u0, nu, s };                   // nFly <= LAG < SLOTS here: the slot about to be reused is never in flight
+        }
+        i++;
     }
     for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(p.st[s]));
     return 0;
+}
+
+template <typename Launch>
+static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* outs, int nOut, size_t nUnits, size_t unitsPerChunk, Launch launch)
+{
+    ChunkClaimer claimer(nUnits, nUnits < unitsPerChunk ? nUnits : unitsPerChunk);
+    return run_chunked_on(p, ins, nIn, outs, nOut, claimer, launch);
 }
 
 template <typename Launch>
@@ -540,16 +571,20 @@ extern "C" int xDct32BatchDev(const int16_t* dSrc, int16_t* dDst, size_t nBlocks
     return 0;
 }
 
+static size_t dct32_chunk(size_t nBlocks)
+{
+    // 32 MiB chunks amortise the per-chunk hand-over best (47.0 GB/s each way of the 48.2 the link gives with both directions busy);
+    // below ~24 chunks the fill and drain of the pipeline cost more than that, so smaller batches use 16 Ki blocks
+    // (profiles/r01_e2e_chunk_sweep.log).
+    const size_t chunk = g_dctChunk.load();
+    return chunk ? chunk : nBlocks >= ((size_t)3 << 18) ? 32768 : 16384;
+}
+
 extern "C" int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2)
 {
     if (!shifts_ok(s1, s2) || (nBlocks && (!src || !dst))) return fail("xDct32Batch", cudaSuccess);
     if (nBlocks == 0) return 0;
-    // 32 MiB chunks amortise the per-chunk hand-over best (47.0 GB/s each way of the 48.2 the link gives with both directions busy);
-    // below ~24 chunks the fill and drain of the pipeline cost more than that, so smaller batches use 16 Ki blocks
-    // (profiles/r01_e2e_chunk_sweep.log).
-    size_t chunk = g_dctChunk.load();
-    if (chunk == 0) chunk = nBlocks >= ((size_t)3 << 18) ? 32768 : 16384;
-    return run_chunked(src, 2048, dst, 2048, nBlocks, chunk,
+    return run_chunked(src, 2048, dst, 2048, nBlocks, dct32_chunk(nBlocks),
                        [&](void* di, void* dO, size_t n, cudaStream_t st) {
                            return dct32_dispatch((const int16_t*)di, (int16_t*)dO, n, s1, s2, st);
                        });
@@ -557,8 +592,10 @@ extern "C" int xDct32Batch(const int16_t* src, int16_t* dst, size_t nBlocks, int
 
 extern "C" int xDct32BatchMultiGpu(const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, int nGpus)
 {
-    // blocks are independent -> GPU g of G owns the contiguous range [g*N/G, (g+1)*N/G); one host
-    // thread per device drives that device's chunked pipeline; no collective, no peer traffic.
+    // blocks are independent, no collective, no peer traffic.  One host thread per device drives that device's
+    // chunked pipeline; the threads claim chunks from ONE shared counter instead of owning a fixed [g*N/G, (g+1)*N/G) range,
+    // because the host links of a box are not equal (on the 8-GPU pool box GPUs 4-7 get 36 GB/s each way, GPUs 0-3 47, and
+    // all of them together 64: profiles/r02_link_ceiling.md) -- a static split finishes with the slowest link.
     int have = 0;
     CK(cudaGetDeviceCount(&have));
     if (nGpus <= 0) nGpus = have;
@@ -566,14 +603,22 @@ extern "C" int xDct32BatchMultiGpu(const int16_t* src, int16_t* dst, size_t nBlo
     if (nBlocks == 0) return 0;
     int prev = 0;
     CK(cudaGetDevice(&prev));
+    // chunks small enough that every GPU gets several, large enough to amortise the hand-over
+    size_t chunk = dct32_chunk(nBlocks / nGpus + 1);
+    ChunkClaimer claimer(nBlocks, chunk < nBlocks ? chunk : nBlocks);
+    const HostArr in{ const_cast<int16_t*>(src), 2048 }, out{ dst, 2048 };
     std::vector<int> rc(nGpus, 0);
     std::vector<std::string> err(nGpus);
     std::vector<std::thread> th;
     for (int g = 0; g < nGpus; g++)
         th.emplace_back([&, g]() {
-            const size_t lo = nBlocks * (size_t)g / nGpus, hi = nBlocks * (size_t)(g + 1) / nGpus;
             if (cudaSetDevice(g) != cudaSuccess) { rc[g] = -1; err[g] = "cudaSetDevice failed"; return; }
-            rc[g] = xDct32Batch(src + lo * 1024, dst + lo * 1024, hi - lo, s1, s2);
+            PipeLease lease;
+            rc[g] = !lease.ok() ? -1
+                  : run_chunked_on(*lease.p, &in, 1, &out, 1, claimer,
+                                   [&](void* const* dI, void* const* dO, size_t, size_t n, cudaStream_t st) {
+                                       return dct32_dispatch((const int16_t*)dI[0], (int16_t*)dO[0], n, s1, s2, st);
+                                   });
             if (rc[g]) err[g] = t_err;
         });
     for (auto& t : th) t.join();
