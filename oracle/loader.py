@@ -55,6 +55,9 @@ class Oracle:
         L.orc_sad.argtypes = [_u8p, C.c_ssize_t, _u8p, C.c_ssize_t, C.c_int, C.c_int]
         L.orc_sad.restype = C.c_uint32
         L.orc_intra32.argtypes = [_u8p, _u8p, C.c_int, _u8p]
+        L.orc_intra32_direct.argtypes = [_u8p, _u8p, C.c_int, _u8p]
+        L.orc_intra_ref_line.argtypes = [_u8p, _u8p, C.c_int, _i32p]
+        L.orc_intra_idx_frac.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_intra32_decide.argtypes = [_u8p, _u8p, _u8p, _u32p, C.c_void_p]
         L.orc_intra_mode_angle.argtypes = [C.c_int]
         L.orc_intra_mode_angle.restype = C.c_int
@@ -138,6 +141,23 @@ class Oracle:
         pred = np.empty((32, 32), np.uint8)
         self.lib.orc_intra32(np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(top, np.uint8), mode, pred)
         return pred
+
+    def intra32_direct(self, left, top, mode):
+        """the second, table-free restatement (per pixel, sample-position form)"""
+        pred = np.empty((32, 32), np.uint8)
+        self.lib.orc_intra32_direct(np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(top, np.uint8), mode, pred)
+        return pred
+
+    def intra_ref_line(self, left, top, mode):
+        """ref[-32..64] of an angular mode as the predictor builds it; -1 = never read"""
+        out = np.empty(97, np.int32)
+        self.lib.orc_intra_ref_line(np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(top, np.uint8), mode, out)
+        return out
+
+    def intra_idx_frac(self, mode, k):
+        idx, f = C.c_int(0), C.c_int(0)
+        self.lib.orc_intra_idx_frac(mode, k, C.byref(idx), C.byref(f))
+        return idx.value, f.value
 
     def intra32_decide(self, cur, left, top):
         cost = np.zeros(35, np.uint32)

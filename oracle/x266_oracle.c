@@ -15,9 +15,16 @@
  *   - DCT 4/8/16: PINNED *through the reference code* by the palindromic-extension identity
  *     (a size-N row repeated as [x, rev x, ...] to 32 samples through the reference
  *     partialButterfly32 with shift + (5-log2N) equals the size-N transform on rows k*32/N).
- *   - Intra32: PARITY UNPINNED.  The reference has no C model and src/mkIntra32-wip.bsv does not
- *     compile; restated from the 35-mode angular definition the BSV tables encode, with the BSV
- *     facTbl/mapShift tables as cross-checks (tests/golden/intra_tables.json).
+ *   - Intra32: NO EXECUTABLE REFERENCE exists (no C model; src/mkIntra32-wip.bsv does not compile), so
+ *     no prediction of the reference can be reproduced and the header keeps saying "parity unpinned"
+ *     for the pixels.  Pinned as far as the reference goes: every table (mapTbl, facTbl, mapShift,
+ *     all rows, by the modes their comments name), every reference-line / inverse-angle projection
+ *     list of getRefPixels (all 18 cases), the interpolator weights and the DC sum are parsed from
+ *     the BSV into tests/golden/intra_bsv.json and this restatement reproduces each; the WIP file's
+ *     defects are listed in the tests as explicit expected differences (two swapped mapTbl entries
+ *     of mode 16, the undefined xL[0] in the corner slot and xT[32] for xL[32] in cases 9-15, the
+ *     live >>6, the truncating and doubled DC shift).  A second, table-free restatement
+ *     (orc_intra32_direct) backs the first on all 35 modes.
  *   - SATD full search / SAD: the search loop is ours (reference has no search loop); the cost of
  *     each candidate is the pinned satd8x8.
  */
@@ -313,6 +320,38 @@ int orc_intra_mode_angle(int mode)          /* mode 2..34 */
     /* modes 2..18 walk +32..-32 (horizontal family, mirrored), 18..34 walk -32..+32 */
 }
 
+/* per-distance index / fraction of an angular mode: k = 0..31 is the distance from the main reference (row for the vertical
+ * family, column for the horizontal one) -- mapTbl / facTbl of the BSV (:75-112) */
+void orc_intra_idx_frac(int mode, int k, int* idx, int* frac)
+{
+    const int t = (k + 1) * orc_intra_mode_angle(mode);
+    *idx = t >> 5;
+    *frac = t & 31;
+}
+
+/* The working reference line of an angular mode, ref[-32..64] stored at out[0..96] (out[32] = ref[0] = the corner); entries the mode
+ * never reads are -1.  Main part = top (vertical family) or corner + left (horizontal family); negative-angle modes extend it
+ * to the left by projecting the side reference with (k*invAngle+128)>>8 -- getRefPixels of the BSV (:135-328). */
+void orc_intra_ref_line(const uint8_t left[64], const uint8_t top[65], int mode, int out[97])
+{
+    const int isVer = mode >= 18;
+    const int ang = orc_intra_mode_angle(mode);
+    int *ref = out + 32, k;
+    for (k = 0; k < 97; k++) out[k] = -1;
+    for (k = 0; k <= 64; k++) ref[k] = isVer ? top[k] : (k == 0 ? top[0] : left[k - 1]);
+    if (ang < 0)
+    {
+        int a, inv = 0;
+        for (k = 33; k <= 64; k++) ref[k] = -1;          /* a negative angle never looks past ref[32] */
+        for (a = 0; a < 8; a++) if (orc_intra_angle[9 + a] == ang) inv = orc_intra_invAngle[a];
+        for (k = -1; k > ((32 * ang) >> 5); k--)          /* lowest index read: x + idx + 1 with x = 0, idx = (32*ang)>>5 */
+        {
+            int s = ((-k) * inv + 128) >> 8;             /* side-reference index 1..32 */
+            ref[k] = isVer ? left[s - 1] : top[s];
+        }
+    }
+}
+
 void orc_intra32(const uint8_t left[64], const uint8_t top[65], int mode, uint8_t pred[32 * 32])
 {
     int x, y;
@@ -334,24 +373,12 @@ void orc_intra32(const uint8_t left[64], const uint8_t top[65], int mode, uint8_
     }
     {
         const int isVer = mode >= 18;
-        const int ang = orc_intra_mode_angle(mode);
-        /* main reference, index -32..64; ref[0] is the corner */
-        int buf[32 + 65], *ref = buf + 32, k;
-        for (k = 0; k <= 64; k++) ref[k] = isVer ? top[k] : (k == 0 ? top[0] : left[k - 1]);
-        if (ang < 0)
+        int buf[97], *ref = buf + 32;
+        orc_intra_ref_line(left, top, mode, buf);
+        for (y = 0; y < 32; y++)                          /* y = distance from the main reference */
         {
-            int a, inv = 0;
-            for (a = 0; a < 8; a++) if (orc_intra_angle[9 + a] == ang) inv = orc_intra_invAngle[a];
-            for (k = -1; k >= ((32 * ang) >> 5); k--)
-            {
-                int s = ((-k) * inv + 128) >> 8;         /* side-reference index 1..32 */
-                ref[k] = isVer ? left[s - 1] : top[s];
-            }
-        }
-        for (y = 0; y < 32; y++)                          /* y = position along the prediction direction */
-        {
-            const int idx = ((y + 1) * ang) >> 5;
-            const int f = ((y + 1) * ang) & 31;
+            int idx, f;
+            orc_intra_idx_frac(mode, y, &idx, &f);
             for (x = 0; x < 32; x++)
             {
                 int v = f ? (((32 - f) * ref[x + idx + 1] + f * ref[x + idx + 2] + 16) >> 5)
@@ -360,6 +387,60 @@ void orc_intra32(const uint8_t left[64], const uint8_t top[65], int mode, uint8_
             }
         }
     }
+}
+
+/* Second, independent restatement of the same predictor (as orc_partialDense backs the butterfly): one pixel at a time, straight
+ * from the sample-position form of the 35-mode definition, no working line and no tables -- p(x, y) below is the neighbouring
+ * sample at picture position (x, y) relative to the block, x = -1 or y = -1. */
+static int orc_nb(const uint8_t left[64], const uint8_t top[65], int x, int y)
+{
+    return y < 0 ? top[x + 1] : left[y];               /* (x, -1) for x = -1..63 | (-1, y) for y = 0..63 */
+}
+
+static int orc_intra_sample(const uint8_t left[64], const uint8_t top[65], int isVer, int angle, int i)
+{
+    /* reference sample number i along the main direction: i >= 0 on the main side (i = 0 is the corner), i < 0 projected from
+     * the side with the inverse angle round(8192 / -angle) */
+    if (i >= 0) return isVer ? orc_nb(left, top, i - 1, -1) : (i == 0 ? orc_nb(left, top, -1, -1) : orc_nb(left, top, -1, i - 1));
+    {
+        const int inv = (8192 * 2 + (-angle)) / (2 * (-angle));       /* rounded 8192/|angle|: 4096 1638 910 630 482 390 315 256 */
+        const int s = ((-i) * inv + 128) >> 8;
+        return isVer ? orc_nb(left, top, -1, s - 1) : orc_nb(left, top, s - 1, -1);
+    }
+}
+
+void orc_intra32_direct(const uint8_t left[64], const uint8_t top[65], int mode, uint8_t pred[32 * 32])
+{
+    static const signed char angle_of_mode[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
+                                                   -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+    int px, py;
+    for (py = 0; py < 32; py++)
+        for (px = 0; px < 32; px++)
+        {
+            int v;
+            if (mode == 0)
+                v = ((31 - px) * orc_nb(left, top, -1, py) + (px + 1) * orc_nb(left, top, 32, -1) +
+                     (31 - py) * orc_nb(left, top, px, -1) + (py + 1) * orc_nb(left, top, -1, 32) + 32) >> 6;
+            else if (mode == 1)
+            {
+                int i, s = 0;
+                for (i = 0; i < 32; i++) s += orc_nb(left, top, i, -1) + orc_nb(left, top, -1, i);
+                v = (s + 32) >> 6;
+            }
+            else
+            {
+                const int isVer = mode >= 18, angle = angle_of_mode[mode];
+                const int dist = isVer ? py : px, along = isVer ? px : py;     /* distance from / position along the main reference */
+                const int disp = (dist + 1) * angle;                           /* displacement in 1/32 sample */
+                const int whole = disp >= 0 ? disp / 32 : -((-disp + 31) / 32); /* floor without relying on >> of a negative */
+                const int part = disp - 32 * whole;
+                const int a = orc_intra_sample(left, top, isVer, angle, along + whole + 1);
+                v = a;
+                if (part)
+                    v = ((32 - part) * a + part * orc_intra_sample(left, top, isVer, angle, along + whole + 2) + 16) / 32;
+            }
+            pred[py * 32 + px] = (uint8_t)v;
+        }
 }
 
 /* Fused intra mode decision ("next" row N1): cost[m] = sum over the 16 8x8 sub-blocks of satd8x8(cur - pred_m). */

@@ -6,7 +6,8 @@
                       running oracle/_ref (= src_tb/dct32.c + src_tb/satd.c compiled in place).
   ref_vectors.npz     small input/output sets produced by the reference itself (random 9/11/16-bit and
                       extreme blocks, the srand(1) BDPI stream of the testbench).
-  intra_tables.json   facTbl / mapShift / mapTbl parsed from src/mkIntra32-wip.bsv:75-132.
+  intra_bsv.json      every table, reference-line / projection list, the interpolator and the DC sum parsed from
+                      src/mkIntra32-wip.bsv:75-132,135-328,352-392 (gen_intra_golden.py).
 """
 import json
 import os
@@ -80,16 +81,9 @@ def main():
         partial_src=line_src, partial_out_shift4_line5=r.partial32(line_src, 4, 5),
         srand1_getDiff=diff, srand1_getDct=words, srand1_satd_rows=rows)
 
-    # intra tables from the BSV
-    src = open(os.path.join(REF_TREE, "src", "mkIntra32-wip.bsv")).read()
-
-    def table(name):
-        m = re.search(name + r"\[\d+\]\[\d+\]\s*=\s*\{(.*?)\};", src, re.S)
-        rows = re.findall(r"\{([^{}]*)\}", m.group(1))
-        return [[int(v) for v in re.findall(r"-?\d+", row)] for row in rows]
-
-    json.dump(dict(mapTbl=table("mapTbl"), facTbl=table("facTbl"), mapShift=table("mapShift")),
-              open(os.path.join(HERE, "intra_tables.json"), "w"))
+    # everything the BSV holds about the intra predictor (tables, projection lists, interpolator, DC): intra_bsv.json
+    import gen_intra_golden
+    gen_intra_golden.main()
     # the reference's own SAD golden dataset (riscv/programs/benchmarks/sad/dataset1.h: two 64x64 inputs + verify_data)
     ds = open(os.path.join(REF_TREE, "riscv", "programs", "benchmarks", "sad", "dataset1.h")).read()
     arrs = re.findall(r"(input_data1|input_data2|verify_data)\[DATA_SIZE\]\s*=\s*\{(.*?)\};", ds, re.S)

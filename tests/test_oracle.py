@@ -147,22 +147,165 @@ def test_sad_matches_riscv_benchmark_definition(orc):
     assert orc.sad(a, b) == int(np.abs(a.astype(int) - b.astype(int)).sum())
 
 
-# ---- intra: parity unpinned; cross-check the restatement against the BSV tables -----------------------
-def test_intra_tables_match_bsv(orc):
-    t = json.load(open(os.path.join(GOLDEN, "intra_tables.json")))
-    fac = t["facTbl"]                   # rows: modes 2..17 (mkIntra32-wip.bsv:95-112)
-    for row, mode in enumerate(range(2, 18)):
-        ang = orc.lib.orc_intra_mode_angle(mode)
-        assert fac[row] == [((k + 1) * ang) & 31 for k in range(32)], mode
-    shift = t["mapShift"]               # rows: modes 34..19, flag k = index changes between row k and k+1
-    for row, mode in enumerate(range(34, 18, -1)):
-        ang = orc.lib.orc_intra_mode_angle(mode)
-        idx = [((k + 1) * ang) >> 5 for k in range(32)]
-        assert shift[row] == [int(idx[k + 1] != idx[k]) for k in range(31)], mode
-    mp = t["mapTbl"]                    # positive-angle rows equal iIdx+... up to the documented typos
-    for row, mode in enumerate(range(3, 10), start=1):
-        ang = orc.lib.orc_intra_mode_angle(mode)
-        assert mp[row] == [((k + 1) * ang) >> 5 for k in range(32)], mode
+# ---- intra: no executable reference exists (the BSV is WIP and does not compile).  Everything the BSV does hold -- the three
+# ---- tables, every reference-line / projection list, the interpolator and the DC sum -- is parsed into tests/golden/intra_bsv.json
+# ---- (gen_intra_golden.py) and the restatement must reproduce each; the WIP file's defects are listed as EXPECTED DIFFERENCES.
+@pytest.fixture(scope="module")
+def bsv():
+    return json.load(open(os.path.join(GOLDEN, "intra_bsv.json")))
+
+
+def _modes_of_label(label):
+    """'Mode  3, 33' -> [3, 33]; 'Mode 18-25' -> [18..25]; '*Mode 10, 26,  1' -> [10, 26, 1]"""
+    out = []
+    for part in label.replace("*", "").replace("Mode", "").split(","):
+        part = part.strip()
+        if "-" in part:
+            lo, hi = part.split("-")
+            out += list(range(int(lo), int(hi) + 1))
+        elif part:
+            out.append(int(part))
+    return out
+
+
+def test_intra_facTbl_every_row_and_label(orc, bsv):
+    """facTbl (mkIntra32-wip.bsv:95-112): row r, entry k = fraction of distance k for EVERY mode its comment names"""
+    rows, labels = bsv["facTbl"]["rows"], bsv["facTbl"]["labels"]
+    assert len(rows) == 16
+    seen = set()
+    for row, label in zip(rows, labels):
+        for mode in _modes_of_label(label):
+            if mode == 1:                        # the comment lists DC next to the zero row: no fraction
+                assert row == [0] * 32
+                continue
+            assert row == [orc.intra_idx_frac(mode, k)[1] for k in range(32)], (label, mode)
+            seen.add(mode)
+    assert seen == set(range(2, 35))             # the 16 rows cover all 33 angular modes
+
+
+def test_intra_mapShift_every_row(orc, bsv):
+    """mapShift (:114-132): flag k of mode m = the integer index changes between distance k and k+1 (1-Shift, 0-Keep)"""
+    rows, labels = bsv["mapShift"]["rows"], bsv["mapShift"]["labels"]
+    assert [_modes_of_label(l)[0] for l in labels] == list(range(34, 18, -1))
+    for row, label in zip(rows, labels):
+        mode = _modes_of_label(label)[0]
+        idx = [orc.intra_idx_frac(mode, k)[0] for k in range(32)]
+        assert row == [abs(idx[k + 1] - idx[k]) for k in range(31)], label
+
+
+# the two swapped entries of the "Mode 16" row (:90): positions 22 and 24 hold 4 and 5, the formula gives 5 and 4
+MAPTBL_EXPECTED_DIFFERENCES = {16: {22: (4, 5), 24: (5, 4)}}
+
+
+def test_intra_mapTbl_every_row(orc, bsv):
+    """mapTbl (:75-93): entry k of a horizontal-family row = position, in the working line getRefPixels builds for that mode, of the
+    first tap of distance k at the first position along the reference:  idx_k - min(idx) for the negative angles (the line starts at
+    the most negative projected sample), idx_k for the positive ones (the line starts at ref[1]); the last row is the position of
+    ref[k] in the REVERSED line of modes 18-25."""
+    rows, labels = bsv["mapTbl"]["rows"], bsv["mapTbl"]["labels"]
+    assert len(rows) == 17
+    diffs = {}
+    for row, label in zip(rows, labels):
+        modes = _modes_of_label(label)
+        if modes == list(range(18, 26)):
+            assert row == [32 - k for k in range(32)]
+            continue
+        mode = modes[0]                          # "Mode 2, 26-34": the row is mode 2's (idx_k = k+1)
+        idx = [orc.intra_idx_frac(mode, k)[0] for k in range(32)]
+        want = [v - min(min(idx), 0) for v in idx]
+        bad = {k: (row[k], want[k]) for k in range(32) if row[k] != want[k]}
+        if bad:
+            diffs[mode] = bad
+    assert diffs == MAPTBL_EXPECTED_DIFFERENCES
+
+
+def _coded_refs():
+    """every reference sample gets its own byte value, so a working line tells which sample each entry came from"""
+    left = np.arange(64, dtype=np.uint8)                 # left[i] = i           (BSV xL[1+i])
+    top = (64 + np.arange(65)).astype(np.uint8)          # top[i]  = 64 + i      (BSV xT[i], xT[0] = corner)
+    return left, top
+
+
+def _bsv_code(entry):
+    kind, i = entry
+    if kind == "T":
+        return 64 + i
+    return i - 1 if i >= 1 else None                      # xL = cons(?, left): xL[0] is an undefined slot (:375)
+
+
+# getRefPixels case -> the mode it serves.  The case labels follow mkIntra's own numbering (:137-323): 0-8 the positive horizontal
+# angles, 9-15 modes 11-17, 16-23 modes 18-25, 24-32 the positive vertical angles, 33 DC.
+REFLINE_CASE_MODE = {**{9 + i: 11 + i for i in range(7)}, **{16 + i: 18 + i for i in range(8)}}
+# Expected differences of the WIP file, same two in each of the seven cases 9-15 (:152,156 ...):
+#  * where ref[0] (the corner) belongs the list has xL[0], the undefined head that `cons(?, x.refs.left)` prepends -> code None
+#  * where ref[32] = left[31] = xL[32] belongs it has xT[32]
+
+
+def test_intra_reference_lines_every_case(orc, bsv):
+    """getRefPixels (:135-328): all 18 cases.  Projection lists of the 14 negative-angle modes = (k*invAngle+128)>>8 as the
+    restatement projects them; main-reference extents of the positive families; DC fill."""
+    left, top = _coded_refs()
+    cases = {c: r["entries"] for r in bsv["ref_lines"] for c in r["cases"]}
+    assert sorted(cases) == list(range(34))
+    for c in range(0, 9):                                 # modes 2..10: the 64 left samples, ascending
+        assert [_bsv_code(e) for e in cases[c]] == list(range(64))
+    for c in range(24, 33):                               # modes 26..34: the 64 top samples after the corner, ascending
+        assert [_bsv_code(e) for e in cases[c]] == [64 + 1 + i for i in range(64)]
+    assert cases[33] == [["dc", 0]] * 32
+    for c, mode in REFLINE_CASE_MODE.items():
+        ref = orc.intra_ref_line(left, top, mode)         # ref[n] at ref[32 + n]
+        lo = min(n for n in range(-32, 65) if ref[32 + n] >= 0)
+        got = [_bsv_code(e) for e in cases[c]]
+        if mode <= 17:                                    # horizontal family: ascending from the most negative sample to ref[32]
+            want = [int(ref[32 + n]) for n in range(lo, 33)]
+            assert len(got) == len(want), (c, mode)
+            diff = {lo + j: (got[j], want[j]) for j in range(len(want)) if got[j] != want[j]}
+            assert diff == {0: (None, 64), 32: (64 + 32, 31)}, (c, mode, diff)          # the two expected differences above
+        else:                                             # vertical family: REVERSED, from ref[32] down to the most negative sample
+            want = [int(ref[32 + n]) for n in range(32, lo - 1, -1)]
+            assert got == want, (c, mode)
+
+
+def test_intra_interpolator_and_dc_against_bsv(orc, bsv):
+    """weights (32 - fac), fac and the rounding constant 16 are the live rule's (:363); the live shift (6) is the known WIP defect,
+    the disabled block rounds with roundN(., 5) (:503) and so does the restatement.  DC: 32 left + 32 top samples (:388-391)."""
+    live = bsv["interp_live"]
+    assert (live["w0"], live["w1"], live["round"], live["shift"]) == ("32 - fac", "fac", 16, 6)
+    assert bsv["interp_disabled_block"]["roundN"] == 5
+    a, b = 37, 203
+    left = np.full(64, a, np.uint8)
+    top = np.full(65, a, np.uint8)
+    for mode in (27, 29, 33):                             # positive vertical: taps top[x+idx+1], top[x+idx+2]; alternate the two values
+        top[:] = np.where(np.arange(65) % 2 == 0, a, b)
+        pred = orc.intra32(left, top, mode)
+        for y in range(32):
+            idx, f = orc.intra_idx_frac(mode, y)
+            for x in (0, 1, 30, 31):
+                t0, t1 = int(top[x + idx + 1]), int(top[x + idx + 2])
+                assert pred[y, x] == ((32 - f) * t0 + f * t1 + live["round"]) >> bsv["interp_disabled_block"]["roundN"]
+    dc = bsv["dc"]
+    assert dc["count"] == 32 and dc["terms"] == ["xL[1+i]", "xT[1+i]"] and dc["mkIntra32_terms"] == ["x.left[i]", "x.top[1+i]"]
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        left, top = rng.integers(0, 256, 64, dtype=np.uint8), rng.integers(0, 256, 65, dtype=np.uint8)
+        s = int(left[:32].sum()) + int(top[1:33].sum())  # xL[1+i] = left[i], xT[1+i] = top[1+i]
+        got = int(orc.intra32(left, top, 1)[0, 0])
+        assert got == (s + 32) >> 6
+        # expected difference: the RTL truncates (sum >> 6, :392) and then shifts the 8-bit value by 6 AGAIN (:318), which would make
+        # every DC block 0..3; the restatement rounds once
+        assert got - (s >> dc["shift"]) in (0, 1) and dc["second_shift_in_getRefPixels"] == 6
+
+
+def test_intra_second_restatement_agrees(orc):
+    """orc_intra32 (working line + per-distance index/fraction) vs orc_intra32_direct (per pixel, sample positions, no tables, no
+    arithmetic shift of negatives): all 35 modes, random / extreme / ramp references"""
+    rng = np.random.default_rng(35)
+    sets = [(rng.integers(0, 256, 64, dtype=np.uint8), rng.integers(0, 256, 65, dtype=np.uint8)) for _ in range(12)]
+    sets += [(np.full(64, v, np.uint8), np.full(65, w, np.uint8)) for v, w in ((0, 255), (255, 0), (255, 255), (0, 0))]
+    sets += [_coded_refs(), (np.arange(64, dtype=np.uint8)[::-1].copy(), (255 - np.arange(65)).astype(np.uint8))]
+    for left, top in sets:
+        for mode in range(35):
+            assert np.array_equal(orc.intra32(left, top, mode), orc.intra32_direct(left, top, mode)), mode
 
 
 def test_intra_simple_modes(orc):
