@@ -166,6 +166,27 @@ int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8_t* dPred, 
  *   bestMode[i] = argmin_m cost[i][m] (ties -> lowest mode).  Prediction and residual never leave the SM. */
 int xIntra32Decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n);
 int xIntra32DecideDev(const uint8_t* dCur, const uint8_t* dRefs, uint32_t* dCost, int32_t* dBestMode, size_t n, void* stream);
+/* The closed intra block loop in ONE kernel ("next" rows N1 + N3; both channels of the RTL's intra unit, `Decide` and `Recon`,
+ * src/mkIntra32-wip.bsv:39-48, around the transform of src_tb/dct32.c:197-198 and its inverse with the same matrix dct32.c:30-64).
+ * For each of n 32x32 blocks (cur[i] = 32x32 u8 row-major, refs[i] as for xIntra32Pred):
+ *   bestMode[i] = the xIntra32Decide decision (cost[i][35] as there; cost may be NULL)
+ *   level[i]    = Q(DCT32(cur - pred_best)), forward shifts 4 / 11 (8-bit video), [32][32] int16
+ *   recon[i]    = clip8(pred_best + IDCT32(Q^-1(level)))   with the inverse shifts 7 / 12, [32][32] u8
+ * Prediction, residual and coefficients never leave the SM: 1 KiB + 129 B in, 2 KiB + 1 KiB + 4 B out per block.
+ * Q is a STUB (the reference has no quantiser): the flat intra quantiser arithmetic of the HEVC/VVC test models for 8-bit video,
+ *   level = sign(c) * min(32767, (|c| * qScale[qp%6] + (171 << (qBits-9))) >> qBits), qBits = 16 + qp/6, qScale = {26214,23302,20560,18396,16384,14564}
+ *   c'    = clip16((level * (iqScale[qp%6] << (qp/6)) + 8) >> 4),                                       iqScale = {40,45,51,57,64,72};  qp in 0..51. */
+int xIntra32EncodeBlock(const uint8_t* cur, const uint8_t* refs, size_t n, int qp, int16_t* level, uint8_t* recon,
+                        int32_t* bestMode, uint32_t* cost);
+int xIntra32EncodeBlockDev(const uint8_t* dCur, const uint8_t* dRefs, size_t n, int qp, int16_t* dLevel, uint8_t* dRecon,
+                           int32_t* dBestMode, uint32_t* dCost, void* stream);
+/* the `Recon` channel alone: mode[i] given (0..34) */
+int xIntra32Recon(const uint8_t* cur, const uint8_t* refs, const uint8_t* mode, size_t n, int qp, int16_t* level, uint8_t* recon);
+int xIntra32ReconDev(const uint8_t* dCur, const uint8_t* dRefs, const uint8_t* dMode, size_t n, int qp, int16_t* dLevel,
+                     uint8_t* dRecon, void* stream);
+/* the quantiser stub on its own: nCoef (multiple of 8) int16 coefficients -> levels and/or de-quantised coefficients (either may be NULL) */
+int xQuantDequantDev(const int16_t* dCoef, int16_t* dLevel, int16_t* dDequant, size_t nCoef, int qp, void* stream);
+
 /* Diagnostic (host only, needs no device): the per-mode MMA fragment table the intra kernel multiplies with, 35 x 256 words,
  * [mode][half][lane][4] -- A fragments of the weight matrix for vertical modes, B fragments of its transpose (output columns
  * permuted, x = 8(n>>1) + 2t + (n&1)) for horizontal modes.  tests/intra_mma_model.py replays the kernel's choreography with it. */

@@ -58,6 +58,10 @@ class Oracle:
         L.orc_intra32_direct.argtypes = [_u8p, _u8p, C.c_int, _u8p]
         L.orc_intra_ref_line.argtypes = [_u8p, _u8p, C.c_int, _i32p]
         L.orc_intra_idx_frac.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_quant.argtypes = [_i16p, _i16p, C.c_size_t, C.c_int]
+        L.orc_dequant.argtypes = [_i16p, _i16p, C.c_size_t, C.c_int]
+        L.orc_intra32_recon.argtypes = [_u8p, _u8p, _u8p, C.c_int, C.c_int, _i16p, _u8p]
+        L.orc_intra32_encode.argtypes = [_u8p, _u8p, _u8p, C.c_int, _i16p, _u8p, _u32p, C.c_void_p]
         L.orc_intra32_decide.argtypes = [_u8p, _u8p, _u8p, _u32p, C.c_void_p]
         L.orc_intra_mode_angle.argtypes = [C.c_int]
         L.orc_intra_mode_angle.restype = C.c_int
@@ -165,6 +169,31 @@ class Oracle:
         self.lib.orc_intra32_decide(np.ascontiguousarray(cur, np.uint8).ravel(), np.ascontiguousarray(left, np.uint8),
                                     np.ascontiguousarray(top, np.uint8), cost, C.byref(best))
         return cost, best.value
+
+    def quant(self, coef, qp):
+        coef = np.ascontiguousarray(coef, np.int16)
+        out = np.empty_like(coef)
+        self.lib.orc_quant(coef.ravel(), out.ravel(), coef.size, qp)
+        return out
+
+    def dequant(self, level, qp):
+        level = np.ascontiguousarray(level, np.int16)
+        out = np.empty_like(level)
+        self.lib.orc_dequant(level.ravel(), out.ravel(), level.size, qp)
+        return out
+
+    def intra32_recon(self, cur, left, top, mode, qp):
+        level = np.empty(1024, np.int16); recon = np.empty(1024, np.uint8)
+        self.lib.orc_intra32_recon(np.ascontiguousarray(cur, np.uint8).ravel(), np.ascontiguousarray(left, np.uint8),
+                                   np.ascontiguousarray(top, np.uint8), mode, qp, level, recon)
+        return level.reshape(32, 32), recon.reshape(32, 32)
+
+    def intra32_encode(self, cur, left, top, qp):
+        level = np.empty(1024, np.int16); recon = np.empty(1024, np.uint8)
+        cost = np.zeros(35, np.uint32); best = C.c_int32(0)
+        self.lib.orc_intra32_encode(np.ascontiguousarray(cur, np.uint8).ravel(), np.ascontiguousarray(left, np.uint8),
+                                    np.ascontiguousarray(top, np.uint8), qp, level, recon, cost, C.byref(best))
+        return level.reshape(32, 32), recon.reshape(32, 32), cost, best.value
 
     # --- tiled frames ----------------------------------------------------------------------
     def conv_input_fmt(self, Y, U, V):

@@ -561,6 +561,69 @@ void orc_fill_residual(int16_t* dst, size_t n, uint64_t seed, int kind)
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * N3 quantiser stub + N1/N3 closed block loop.  NOT IN THE REFERENCE: the arithmetic is that of the HEVC/VVC test
+ * models' flat intra quantiser for 8-bit video and a 32x32 transform (transformShift = 15 - 8 - 5 = 2):
+ *   level = sign(c) * min(32767, (|c| * qScale[qp%6] + (171 << (qBits-9))) >> qBits),  qBits = 14 + qp/6 + 2
+ *   c'    = clip16((level * (iqScale[qp%6] << (qp/6)) + 8) >> 4)
+ * and the loop is  decide (orc_intra32_decide) -> best-mode prediction (orc_intra32) -> residual -> orc_dct2d(4, 11) -> quantise
+ * -> de-quantise -> orc_idct2d(7, 12) -> recon = clip8(pred + residual').
+ * ---------------------------------------------------------------------------------------------- */
+static const int orc_qScale[6]  = { 26214, 23302, 20560, 18396, 16384, 14564 };
+static const int orc_iqScale[6] = { 40, 45, 51, 57, 64, 72 };
+
+void orc_quant(const int16_t* coef, int16_t* level, size_t n, int qp)
+{
+    const int qBits = 16 + qp / 6;
+    const int64_t add = (int64_t)171 << (qBits - 9);
+    size_t i;
+    for (i = 0; i < n; i++)
+    {
+        const int c = coef[i];
+        int64_t a = (((int64_t)(c < 0 ? -c : c) * orc_qScale[qp % 6] + add) >> qBits);
+        if (a > 32767) a = 32767;
+        level[i] = (int16_t)(c < 0 ? -a : a);
+    }
+}
+
+void orc_dequant(const int16_t* level, int16_t* coef, size_t n, int qp)
+{
+    const int64_t scale = (int64_t)orc_iqScale[qp % 6] << (qp / 6);
+    size_t i;
+    for (i = 0; i < n; i++)
+    {
+        int64_t v = (level[i] * scale + 8) >> 4;
+        coef[i] = (int16_t)(v > 32767 ? 32767 : v < -32768 ? -32768 : v);
+    }
+}
+
+/* the `Recon` channel (mkIntra32-wip.bsv:39-48): mode given */
+void orc_intra32_recon(const uint8_t cur[1024], const uint8_t left[64], const uint8_t top[65], int mode, int qp,
+                       int16_t level[1024], uint8_t recon[1024])
+{
+    uint8_t pred[1024];
+    int16_t resi[1024], coef[1024], dq[1024], back[1024];
+    int i;
+    orc_intra32(left, top, mode, pred);
+    for (i = 0; i < 1024; i++) resi[i] = (int16_t)(cur[i] - pred[i]);
+    orc_dct2d(resi, coef, 5, 4, 11);
+    orc_quant(coef, level, 1024, qp);
+    orc_dequant(level, dq, 1024, qp);
+    orc_idct2d(dq, back, 5, 7, 12);
+    for (i = 0; i < 1024; i++)
+    {
+        const int v = pred[i] + back[i];
+        recon[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+    }
+}
+
+void orc_intra32_encode(const uint8_t cur[1024], const uint8_t left[64], const uint8_t top[65], int qp,
+                        int16_t level[1024], uint8_t recon[1024], uint32_t cost[35], int32_t* bestMode)
+{
+    orc_intra32_decide(cur, left, top, cost, bestMode);
+    orc_intra32_recon(cur, left, top, *bestMode, qp, level, recon);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Batch drivers with a pthread fan-out over contiguous ranges (CPU baseline "port" when the real
  * reference library oracle/_ref is not available).
  * ---------------------------------------------------------------------------------------------- */

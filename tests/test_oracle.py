@@ -456,3 +456,30 @@ def test_search_tile_decomposition_covers_every_candidate_once(R, bw):
                     assert p - 8 * i == mx and 0 <= mx <= 2 * R and p < npos
                     seen[(i, mx)] = seen.get((i, mx), 0) + 1
     assert len(seen) == bw * (2 * R + 1) and set(seen.values()) == {1}
+
+
+# ---- quantiser stub + closed block loop (not in the reference: properties of the restatement) -------------------------------
+def test_quant_stub_properties(orc):
+    c = np.arange(-32767, 32768, dtype=np.int32).astype(np.int16)
+    for qp in (0, 4, 22, 51):
+        lv = orc.quant(c, qp).astype(np.int32)
+        assert (np.sign(lv) * np.sign(c) >= 0).all() and (np.diff(lv) >= 0).all()          # sign kept, monotone
+        assert np.array_equal(lv, -lv[::-1])                                                 # odd
+        step = 4.0 * 2.0 ** ((qp - 4) / 6.0)          # quantiser step in coefficient units (transformShift = 2)
+        dq = orc.dequant(lv.astype(np.int16), qp).astype(np.int32)
+        inside = np.abs(dq) < 32767                    # away from the int16 clip of the de-quantiser
+        assert np.abs(dq - c)[inside].max() <= 0.75 * step + 1, qp                           # dead zone 171/512: at most 2/3 of a step
+    # qp 22: step 32, dead zone (1 - 171/512) * 32 = 21.3
+    assert orc.quant(np.array([0, 21, 22, -22, 53, 54], np.int16), 22).tolist() == [0, 0, 1, -1, 1, 2]
+
+
+def test_recon_loop_closes(orc):
+    """at qp 0 the reconstruction of a block whose prediction is good is within a few grey levels of the source"""
+    rng = np.random.default_rng(1)
+    refs = rng.integers(0, 256, 129, dtype=np.uint8)
+    pred = orc.intra32(refs[:64], refs[64:], 26).astype(np.int32)
+    cur = np.clip(pred + rng.integers(-20, 21, (32, 32)), 0, 255).astype(np.uint8)
+    level, recon, cost, best = orc.intra32_encode(cur, refs[:64], refs[64:], 0)
+    assert np.abs(recon.astype(np.int32) - cur).max() <= 3
+    level51, recon51, _, _ = orc.intra32_encode(cur, refs[:64], refs[64:], 51)
+    assert np.count_nonzero(level51) < np.count_nonzero(level) and np.abs(recon51.astype(np.int32) - cur).mean() < 25

@@ -69,6 +69,11 @@ def lib():
     L.xFrameResiDct32Dev.argtypes = [vp, vp, i, i, vp, i, i, vp]
     L.xIntra32Decide.argtypes = [vp, vp, vp, vp, sz]
     L.xIntra32DecideDev.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.xIntra32EncodeBlock.argtypes = [vp, vp, sz, i, vp, vp, vp, vp]
+    L.xIntra32EncodeBlockDev.argtypes = [vp, vp, sz, i, vp, vp, vp, vp, vp]
+    L.xIntra32Recon.argtypes = [vp, vp, vp, sz, i, vp, vp]
+    L.xIntra32ReconDev.argtypes = [vp, vp, vp, sz, i, vp, vp, vp]
+    L.xQuantDequantDev.argtypes = [vp, vp, vp, sz, i, vp]
     L.xTranspose32x32Batch.argtypes = [vp, vp, sz]
     L.xTranspose32x32BatchDev.argtypes = [vp, vp, sz, vp]
     L.sad.argtypes = [vp, vp, sz]
@@ -233,6 +238,45 @@ def xIntra32Decide(cur, refs):
     best = np.empty(cur.shape[0], np.int32)
     _ck(lib().xIntra32Decide(cur.ctypes.data, refs.ctypes.data, cost.ctypes.data, best.ctypes.data, cur.shape[0]), "xIntra32Decide")
     return cost, best
+
+
+def xIntra32EncodeBlock(cur, refs, qp, want_cost=True):
+    """fused decide -> predict -> residual -> DCT32 -> quant/dequant -> IDCT32 -> recon: (level, recon, bestMode, cost)"""
+    cur = _np(cur, np.uint8).reshape(-1, 1024)
+    refs = _np(refs, np.uint8).reshape(-1, 129)
+    n = cur.shape[0]
+    assert refs.shape[0] == n
+    level = np.empty((n, 32, 32), np.int16)
+    recon = np.empty((n, 32, 32), np.uint8)
+    best = np.empty(n, np.int32)
+    cost = np.empty((n, 35), np.uint32) if want_cost else None
+    _ck(lib().xIntra32EncodeBlock(cur.ctypes.data, refs.ctypes.data, n, qp, level.ctypes.data, recon.ctypes.data, best.ctypes.data,
+                                  cost.ctypes.data if want_cost else None), "xIntra32EncodeBlock")
+    return level, recon, best, cost
+
+
+def xIntra32EncodeBlockDev(d_cur, d_refs, n, qp, d_level, d_recon, d_best, d_cost=0, stream=0):
+    _ck(lib().xIntra32EncodeBlockDev(d_cur, d_refs, n, qp, d_level, d_recon, d_best, d_cost, stream), "xIntra32EncodeBlockDev")
+
+
+def xIntra32Recon(cur, refs, modes, qp):
+    cur = _np(cur, np.uint8).reshape(-1, 1024)
+    refs = _np(refs, np.uint8).reshape(-1, 129)
+    modes = _np(modes, np.uint8).ravel()
+    n = cur.shape[0]
+    assert refs.shape[0] == n == modes.size
+    level = np.empty((n, 32, 32), np.int16)
+    recon = np.empty((n, 32, 32), np.uint8)
+    _ck(lib().xIntra32Recon(cur.ctypes.data, refs.ctypes.data, modes.ctypes.data, n, qp, level.ctypes.data, recon.ctypes.data), "xIntra32Recon")
+    return level, recon
+
+
+def xIntra32ReconDev(d_cur, d_refs, d_modes, n, qp, d_level, d_recon, stream=0):
+    _ck(lib().xIntra32ReconDev(d_cur, d_refs, d_modes, n, qp, d_level, d_recon, stream), "xIntra32ReconDev")
+
+
+def xQuantDequantDev(d_coef, d_level, d_dq, n_coef, qp, stream=0):
+    _ck(lib().xQuantDequantDev(d_coef, d_level, d_dq, n_coef, qp, stream), "xQuantDequantDev")
 
 
 def xIntra32DecideDev(d_cur, d_refs, d_cost, d_best, n, stream=0):

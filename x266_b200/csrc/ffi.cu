@@ -49,7 +49,7 @@ constexpr int MAX_DEV = 64;
 constexpr int SLOTS = 4;            // chunks in flight per pipeline
 constexpr int LAG = 2;              // a staged chunk is copied out to the caller LAG iterations after it was enqueued (LAG < SLOTS)
 constexpr int MAX_PIPES = 4;        // concurrent host-pointer calls per device; further callers wait
-constexpr int MAX_ARR = 2;          // host arrays per direction of one call
+constexpr int MAX_ARR = 4;          // host arrays per direction of one call
 
 // One pipeline = what ONE host-pointer call needs: SLOTS streams with their device slots, the pinned staging ring of the
 // pageable path and a buffer for call-wide inputs.  A call leases a pipeline for its duration, so two host threads on one
@@ -875,6 +875,69 @@ extern "C" int xIntra32Decide(const uint8_t* cur, const uint8_t* refs, uint32_t*
                        [&](void* const* dI, void* const* dO, size_t, size_t np, cudaStream_t st) {
                            return launch_intra32_decide((const uint8_t*)dI[0], (const uint8_t*)dI[1], (uint32_t*)dO[0], (int32_t*)dO[1], np, st);
                        });
+}
+
+// ---- "next" rows N1 + N3: the closed intra block loop ----------------------------------------------------
+extern "C" int xIntra32EncodeBlockDev(const uint8_t* dCur, const uint8_t* dRefs, size_t n, int qp, int16_t* dLevel, uint8_t* dRecon,
+                                      int32_t* dBestMode, uint32_t* dCost, void* stream)
+{
+    if (qp < 0 || qp > 51 || (n && (!dCur || !dRefs || !dLevel || !dRecon || !dBestMode))) return fail("xIntra32EncodeBlockDev", cudaSuccess);
+    if ((reinterpret_cast<uintptr_t>(dCur) & 7) || (reinterpret_cast<uintptr_t>(dLevel) & 15) || (reinterpret_cast<uintptr_t>(dRecon) & 7))
+        return fail("xIntra32EncodeBlockDev: alignment (cur 8, level 16, recon 8 bytes)", cudaSuccess);
+    if (dev_ready()) return -1;
+    CK(launch_intra32_encode(dCur, dRefs, n, qp, dLevel, dRecon, dBestMode, dCost, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xIntra32EncodeBlock(const uint8_t* cur, const uint8_t* refs, size_t n, int qp, int16_t* level, uint8_t* recon,
+                                   int32_t* bestMode, uint32_t* cost)
+{
+    if (qp < 0 || qp > 51 || (n && (!cur || !refs || !level || !recon || !bestMode))) return fail("xIntra32EncodeBlock", cudaSuccess);
+    if (n == 0) return 0;
+    const HostArr ins[2] = { { const_cast<uint8_t*>(cur), 1024 }, { const_cast<uint8_t*>(refs), 129 } };
+    const HostArr outs[4] = { { level, 2048 }, { recon, 1024 }, { bestMode, 4 }, { cost, 35 * 4 } };
+    return run_chunked(ins, 2, outs, 4, n, (size_t)1 << 13,
+                       [&](void* const* dI, void* const* dO, size_t, size_t np, cudaStream_t st) {
+                           return launch_intra32_encode((const uint8_t*)dI[0], (const uint8_t*)dI[1], np, qp, (int16_t*)dO[0], (uint8_t*)dO[1],
+                                                        (int32_t*)dO[2], (uint32_t*)dO[3], st);
+                       });
+}
+
+extern "C" int xIntra32Recon(const uint8_t* cur, const uint8_t* refs, const uint8_t* mode, size_t n, int qp, int16_t* level, uint8_t* recon)
+{
+    if (qp < 0 || qp > 51 || (n && (!cur || !refs || !mode || !level || !recon))) return fail("xIntra32Recon", cudaSuccess);
+    for (size_t i = 0; i < n; i++)
+        if (mode[i] > 34) return fail("xIntra32Recon: mode > 34", cudaSuccess);
+    if (n == 0) return 0;
+    const HostArr ins[3] = { { const_cast<uint8_t*>(cur), 1024 }, { const_cast<uint8_t*>(refs), 129 }, { const_cast<uint8_t*>(mode), 1 } };
+    const HostArr outs[2] = { { level, 2048 }, { recon, 1024 } };
+    return run_chunked(ins, 3, outs, 2, n, (size_t)1 << 13,
+                       [&](void* const* dI, void* const* dO, size_t, size_t np, cudaStream_t st) {
+                           return launch_intra32_recon((const uint8_t*)dI[0], (const uint8_t*)dI[1], (const uint8_t*)dI[2], np, qp,
+                                                       (int16_t*)dO[0], (uint8_t*)dO[1], st);
+                       });
+}
+
+extern "C" int xIntra32ReconDev(const uint8_t* dCur, const uint8_t* dRefs, const uint8_t* dMode, size_t n, int qp, int16_t* dLevel,
+                                uint8_t* dRecon, void* stream)
+{
+    if (qp < 0 || qp > 51 || (n && (!dCur || !dRefs || !dMode || !dLevel || !dRecon))) return fail("xIntra32ReconDev", cudaSuccess);
+    if ((reinterpret_cast<uintptr_t>(dCur) & 7) || (reinterpret_cast<uintptr_t>(dLevel) & 15) || (reinterpret_cast<uintptr_t>(dRecon) & 7))
+        return fail("xIntra32ReconDev: alignment (cur 8, level 16, recon 8 bytes)", cudaSuccess);
+    if (dev_ready()) return -1;
+    if (check_modes_dev("xIntra32ReconDev", dMode, n, (cudaStream_t)stream)) return -1;
+    CK(launch_intra32_recon(dCur, dRefs, dMode, n, qp, dLevel, dRecon, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xQuantDequantDev(const int16_t* dCoef, int16_t* dLevel, int16_t* dDequant, size_t nCoef, int qp, void* stream)
+{
+    if (qp < 0 || qp > 51 || (nCoef & 7) || (nCoef && (!dCoef || (!dLevel && !dDequant)))) return fail("xQuantDequantDev", cudaSuccess);
+    if ((reinterpret_cast<uintptr_t>(dCoef) | reinterpret_cast<uintptr_t>(dLevel) | reinterpret_cast<uintptr_t>(dDequant)) & 15)
+        return fail("xQuantDequantDev: 16-byte alignment", cudaSuccess);
+    if (dev_ready()) return -1;
+    CK(launch_quant_dequant(dCoef, dLevel, dDequant, nCoef, qp, (cudaStream_t)stream));
+    return 0;
 }
 
 // ---- "next" rows: the encoder's tiled frame format on the device ---------------------------------------

@@ -7,29 +7,12 @@
 // One warp per prediction, 4 output pixels per lane per step, 128-byte coalesced stores.
 #include "common.cuh"
 #include "kernels.h"
+#include "intra_dev.cuh"
 
 #include <mutex>
 #include <vector>
 
 namespace x266 {
-
-__constant__ int c_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
-                                      -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
-// 8192/|angle| rounded, for angle = -2,-5,-9,-13,-17,-21,-26,-32
-__constant__ int c_intraInv[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
-// the same per mode (0 where the angle is not negative)
-__constant__ int c_intraInvMode[35] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4096, 1638, 910, 630, 482, 390, 315,
-                                        256, 315, 390, 482, 630, 910, 1638, 4096, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-
-__device__ __forceinline__ uint32_t intra_row4(uint32_t a, uint32_t b, int f)
-{
-    // 4 pixels: ((32-f)*a + f*b + 16) >> 5 per byte, two 16-bit lanes per multiply-add
-    const uint32_t ae = a & 0x00FF00FFu, ao = (a >> 8) & 0x00FF00FFu;
-    const uint32_t be = b & 0x00FF00FFu, bo = (b >> 8) & 0x00FF00FFu;
-    const uint32_t pe = ((ae * (uint32_t)(32 - f) + be * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
-    const uint32_t po = ((ao * (uint32_t)(32 - f) + bo * (uint32_t)f + 0x00100010u) >> 5) & 0x00FF00FFu;
-    return pe | (po << 8);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Tensor-core form of the angular modes with a fractional angle (|angle| < 32, modes 3..17 and 19..33).
@@ -155,75 +138,6 @@ static const uint32_t* intra_mma_table_dev(cudaError_t* err)
 // The reference line ref[-32..65] lives in a per-warp shared-memory strip; VER selects which of
 // (row, column) is the distance from the main reference so that the loop-invariant index/fraction
 // computations are hoisted (per row for vertical modes, per lane for horizontal modes).
-constexpr int INTRA_WARPS = 8;
-constexpr int INTRA_STRIP = 112;            // 32 (negative part) + 66 + padding, multiple of 16
-
-// Angular modes, SWAR: lane l generates, for it = 0,1, the 16 pixels (row 16*it + (l>>1), columns 16*(l&1)..+15) of
-// the vertical-family prediction P_v (distance = row, position along the main reference = column): one (idx, f)
-// pair per row, 5 aligned words of the reference strip re-aligned with funnel shifts, 2 pixels per multiply-add.
-// Vertical modes store the four words directly (512 contiguous bytes per warp store).  Horizontal modes are
-// P_v^T of the left reference: the rows go through a padded per-warp tile and are read back as columns.
-// 16 pixels of one prediction row from 17 reference bytes starting at byte `sh/8` of p[0], 9 instructions per 4 pixels:
-// the weights are pre-scaled by 8 so that ((32-f)a + f b + 16) >> 5 is the HIGH byte of each 16-bit lane and the final
-// shift-and-mask folds into the byte permute that interleaves the even and odd pixels.  With the aligned bytes a0..a4,
-// E0 = (a0,a2), O = (a1,a3), E1 = (a2,a4) (16-bit lanes):  even pixels = E0*w0 + O*w1,  odd pixels = O*w0 + E1*w1,
-// and E1 is one permute of this word's and the next word's E0.
-__device__ __forceinline__ void intra_row16(const uint32_t* __restrict__ p, int sh, int f, uint32_t (&out)[4])
-{
-    const uint32_t x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
-    uint32_t E[5];
-    const uint32_t A0 = __funnelshift_r(x0, x1, sh), A1 = __funnelshift_r(x1, x2, sh), A2 = __funnelshift_r(x2, x3, sh),
-                   A3 = __funnelshift_r(x3, x4, sh), A4 = x4 >> sh;
-    E[0] = A0 & 0x00FF00FFu; E[1] = A1 & 0x00FF00FFu; E[2] = A2 & 0x00FF00FFu; E[3] = A3 & 0x00FF00FFu; E[4] = A4 & 0x00FF00FFu;
-    const uint32_t A[4] = { A0, A1, A2, A3 };
-    const uint32_t w0 = (uint32_t)(32 - f) * 8u, w1 = (uint32_t)f * 8u;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t O = __byte_perm(A[j], 0u, 0x4341);
-        const uint32_t E1 = __byte_perm(E[j], E[j + 1], 0x5432);
-        const uint32_t pe = E[j] * w0 + (O * w1 + 0x00800080u);
-        const uint32_t po = O * w0 + (E1 * w1 + 0x00800080u);
-        out[j] = __byte_perm(pe, po, 0x7351);
-    }
-}
-
-// the same for 8 pixels (9 reference bytes): used by the mode-decision kernel, whose A fragments are 8-pixel row pieces
-__device__ __forceinline__ void intra_row8(const uint32_t* __restrict__ p, int sh, int f, uint32_t& out0, uint32_t& out1)
-{
-    const uint32_t x0 = p[0], x1 = p[1], x2 = p[2];
-    const uint32_t A0 = __funnelshift_r(x0, x1, sh), A1 = __funnelshift_r(x1, x2, sh), A2 = x2 >> sh;
-    const uint32_t E0 = A0 & 0x00FF00FFu, E1 = A1 & 0x00FF00FFu, E2 = A2 & 0x00FF00FFu;
-    const uint32_t w0 = (uint32_t)(32 - f) * 8u, w1 = (uint32_t)f * 8u;
-    const uint32_t O0 = __byte_perm(A0, 0u, 0x4341), O1 = __byte_perm(A1, 0u, 0x4341);
-    const uint32_t S0 = __byte_perm(E0, E1, 0x5432), S1 = __byte_perm(E1, E2, 0x5432);
-    out0 = __byte_perm(E0 * w0 + (O0 * w1 + 0x00800080u), O0 * w0 + (S0 * w1 + 0x00800080u), 0x7351);
-    out1 = __byte_perm(E1 * w0 + (O1 * w1 + 0x00800080u), O1 * w0 + (S1 * w1 + 0x00800080u), 0x7351);
-}
-
-// Angular modes: lane l generates, for it = 0,1, the 16 pixels (row 16*it + (l>>1), columns 16*(l&1)..+15) of the
-// vertical-family prediction P_v (distance = row, position along the main reference = column): one (idx, f) pair per
-// row.  Vertical modes store the four words directly (512 contiguous bytes per warp store).  Horizontal modes are
-// P_v^T of the left reference: the rows go through a padded per-warp tile and come back as 4x4 byte blocks that are
-// transposed in registers (8 PRMT per block).
-__device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ strip32, int ref0, int ang, int lane, uint32_t (&w)[2][4])
-{
-#pragma unroll
-    for (int it = 0; it < 2; it++) {
-        const int row = 16 * it + (lane >> 1), half = lane & 1;
-        const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
-        const int o = ref0 + 16 * half + idx + 1;                   // byte offset of ref[16*half + idx + 1] in the strip
-        if ((ang & 31) == 0) {                                      // modes 2, 10, 18, 26, 34: every fraction is 0, rows are copies
-            const uint32_t* p = strip32 + (o >> 2);
-            const int sh = (o & 3) * 8;
-            const uint32_t x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
-            w[it][0] = __funnelshift_r(x0, x1, sh); w[it][1] = __funnelshift_r(x1, x2, sh);
-            w[it][2] = __funnelshift_r(x2, x3, sh); w[it][3] = __funnelshift_r(x3, x4, sh);
-        } else {
-            intra_row16(strip32 + (o >> 2), (o & 3) * 8, f, w[it]);
-        }
-    }
-}
-
 template <bool ALIGNED>
 __global__ void __launch_bounds__(INTRA_WARPS * 32)
 intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ modes, uint8_t* __restrict__ pred, size_t n,
@@ -442,7 +356,6 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
 // Neither the prediction nor the residual ever reaches HBM (1 KiB + 129 B in, 35 x 4 B out per block).
 // One CTA per block; a half-warp owns one mode at a time, lane <-> 8x8 sub-block.
 // ------------------------------------------------------------------------------------------------
-constexpr int IDEC_WARPS = 8;
 
 template <int STRIDE>
 __device__ __forceinline__ void had8i(int* v)
@@ -567,150 +480,17 @@ __global__ void __launch_bounds__(IDEC_WARPS * 32, 2)
 intra32_decide_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refs, uint32_t* __restrict__ cost,
                          int32_t* __restrict__ bestMode, size_t n)
 {
-    __shared__ __align__(16) uint8_t scur[2][1024];                 // [0] = block, [1] = its transpose
-    __shared__ __align__(16) int stc[2][32 * 32];                   // T(cur), T(cur^T) in accumulator layout
-    __shared__ __align__(16) uint8_t sraw[144];
-    __shared__ __align__(16) uint8_t strip[IDEC_WARPS][INTRA_STRIP + 16];
-    __shared__ uint32_t scost[35];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, q = lane & 3;
-    const int cZero[4] = { 0, 0, 0, 0 };
-
-    // +-1 matrix fragments, identical to satd8x8_imma_kernel: K position 16r+4q+i <-> sample 32s+8q+4r+i, column 8t+g
+    __shared__ DecideSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31;
     uint32_t B[2][8][2];
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-        for (int t = 0; t < 8; t++)
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int pix = 32 * s + 8 * q + 4 * r + i, nn = 8 * t + g;
-                    v |= ((__popc(nn & pix) & 1) ? 0xFFu : 0x01u) << (8 * i);
-                }
-                B[s][t][r] = v;
-            }
-
-    // this lane's rows: sub-blocks g and g+8 (same column band sx), sub-block rows q and 4+q
-    const int sx = (g & 3) * 8;
-    const int syA = (g >> 2) * 8, syB = syA + 16;
-    uint8_t* sref = strip[warp] + 32 + 4;            // sref[i] = ref[i]; +4 keeps sref-32 word aligned
-    const uint32_t* strip32 = reinterpret_cast<const uint32_t*>(strip[warp]);
-
+    decide_hadamard_fragments(B, lane >> 2, lane & 3);
     for (size_t p = blockIdx.x; p < n; p += gridDim.x) {
-        {
-            const uint32_t w = reinterpret_cast<const uint32_t*>(cur + p * 1024)[tid];
-            reinterpret_cast<uint32_t*>(scur[0])[tid] = w;
-            const int row = tid >> 3, c0 = (tid & 7) * 4;
-#pragma unroll
-            for (int i = 0; i < 4; i++) scur[1][(c0 + i) * 32 + row] = (uint8_t)(w >> (8 * i));
-            if (tid < 129) sraw[tid] = refs[p * 129 + tid];
-        }
-        __syncthreads();
-        if (warp < 2) {                               // T(cur) (warp 0) and T(cur^T) (warp 1)
-            uint32_t A[2][4];
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const uint2 ra = *reinterpret_cast<const uint2*>(&scur[warp][(syA + 4 * s + q) * 32 + sx]);
-                const uint2 rb = *reinterpret_cast<const uint2*>(&scur[warp][(syB + 4 * s + q) * 32 + sx]);
-                A[s][0] = ra.x; A[s][2] = ra.y; A[s][1] = rb.x; A[s][3] = rb.y;
-            }
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                int d[4];
-                mma_u8s8(d, A[0], B[0][t][0], B[0][t][1], cZero);
-                mma_u8s8(d, A[1], B[1][t][0], B[1][t][1], d);
-#pragma unroll
-                for (int c = 0; c < 4; c++) stc[warp][(t * 4 + c) * 32 + lane] = d[c];
-            }
-        }
-        __syncthreads();
-        const uint8_t* left = sraw;
-        const uint8_t* top = sraw + 64;
-
-        for (int mode = warp; mode < 35; mode += IDEC_WARPS) {
-            const bool isVer = mode >= 18;
-            const int ang = c_intraAngle[mode];
-            uint32_t A[2][4];
-            if (mode >= 2) {
-                __syncwarp();
-                for (int i = lane; i <= 71; i += 32) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
-                if (ang < 0) {
-                    int inv = 0;
-#pragma unroll
-                    for (int a = 0; a < 8; a++) if (c_intraAngle[11 + a] == ang) inv = c_intraInv[a];
-                    const int k = lane + 1;
-                    if (-k >= ang) {
-                        const int sidx = (k * inv + 128) >> 8;
-                        sref[-k] = isVer ? left[sidx - 1] : top[sidx];
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int s = 0; s < 2; s++)
-#pragma unroll
-                    for (int sel = 0; sel < 2; sel++) {
-                        const int row = (sel ? syB : syA) + 4 * s + q;             // distance from the main reference
-                        const int t = (row + 1) * ang, idx = t >> 5, f = t & 31;
-                        const int o = 32 + 4 + sx + idx + 1;                        // byte offset of ref[sx+idx+1] in the strip
-                        intra_row8(strip32 + (o >> 2), (o & 3) * 8, f, A[s][sel], A[s][2 + sel]);
-                    }
-            } else if (mode == 1) {
-                int sum = left[lane] + top[1 + lane];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                const uint32_t dc = (uint32_t)((sum + 32) >> 6) * 0x01010101u;
-#pragma unroll
-                for (int s = 0; s < 2; s++)
-#pragma unroll
-                    for (int r = 0; r < 4; r++) A[s][r] = dc;
-            } else {
-                const int tr = top[33], bl = left[32];
-#pragma unroll
-                for (int s = 0; s < 2; s++)
-#pragma unroll
-                    for (int sel = 0; sel < 2; sel++) {
-                        const int row = (sel ? syB : syA) + 4 * s + q;
-                        uint32_t wlo = 0, whi = 0;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            const int col = sx + c;
-                            const uint32_t v = (uint32_t)(((31 - col) * left[row] + (col + 1) * tr + (31 - row) * top[1 + col] + (row + 1) * bl + 32) >> 6);
-                            if (c < 4) wlo |= v << (8 * c); else whi |= v << (8 * (c - 4));
-                        }
-                        A[s][sel] = wlo;
-                        A[s][2 + sel] = whi;
-                    }
-            }
-            // T(pred) for the 16 sub-blocks, |T(cur) - T(pred)| against the parked transform (transposed one for 2..17)
-            const int* tc = stc[(mode >= 2 && !isVer) ? 1 : 0];
-            unsigned sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                int d[4];
-                mma_u8s8(d, A[0], B[0][t][0], B[0][t][1], cZero);
-                mma_u8s8(d, A[1], B[1][t][0], B[1][t][1], d);
-                sa0 = __sad(d[0], tc[(t * 4 + 0) * 32 + lane], sa0);
-                sa1 = __sad(d[1], tc[(t * 4 + 1) * 32 + lane], sa1);
-                sb0 = __sad(d[2], tc[(t * 4 + 2) * 32 + lane], sb0);
-                sb1 = __sad(d[3], tc[(t * 4 + 3) * 32 + lane], sb1);
-            }
-            unsigned sadA = sa0 + sa1, sadB = sb0 + sb1;                // sub-blocks g and g+8, partial over this lane's columns
-            sadA += __shfl_xor_sync(0xffffffffu, sadA, 1); sadB += __shfl_xor_sync(0xffffffffu, sadB, 1);
-            sadA += __shfl_xor_sync(0xffffffffu, sadA, 2); sadB += __shfl_xor_sync(0xffffffffu, sadB, 2);
-            unsigned c4 = q == 0 ? ((sadA + 2) >> 2) + ((sadB + 2) >> 2) : 0u;
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) c4 += __shfl_xor_sync(0xffffffffu, c4, o);
-            if (lane == 0) scost[mode] = c4;
-        }
-        __syncthreads();
-        if (tid < 35) cost[p * 35 + tid] = scost[tid];
+        decide_block(sm, B, cur + p * 1024, refs + p * 129, tid);
+        if (tid < 35) cost[p * 35 + tid] = sm.scost[tid];
         if (tid == 0) {
-            unsigned bc = scost[0];
+            unsigned bc = sm.scost[0];
             int bm = 0;
-            for (int m = 1; m < 35; m++) if (scost[m] < bc) { bc = scost[m]; bm = m; }
+            for (int m = 1; m < 35; m++) if (sm.scost[m] < bc) { bc = sm.scost[m]; bm = m; }
             bestMode[p] = bm;
         }
         __syncthreads();

@@ -54,6 +54,12 @@ cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, 
 cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                  size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
 cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st);
+// encode.cu: the closed intra block loop (decide -> predict -> residual -> DCT32 -> quant/dequant stub -> IDCT32 -> reconstruction)
+cudaError_t launch_intra32_encode(const uint8_t* cur, const uint8_t* refs, size_t n, int qp, int16_t* level, uint8_t* recon,
+                                  int32_t* bestMode, uint32_t* cost, cudaStream_t st);
+cudaError_t launch_intra32_recon(const uint8_t* cur, const uint8_t* refs, const uint8_t* mode, size_t n, int qp, int16_t* level,
+                                 uint8_t* recon, cudaStream_t st);
+cudaError_t launch_quant_dequant(const int16_t* coef, int16_t* level, int16_t* dq, size_t nCoef, int qp, cudaStream_t st);
 cudaError_t intra_device_init();   // uploads the intra fragment table to the current device (called once per device by ffi.cu: ctx_get)
 void intra_device_free();          // releases it (xGpuFree)
 // debug (xGpuTune 15): *bad += number of mode[i] > maxMode
