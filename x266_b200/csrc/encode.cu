@@ -18,7 +18,7 @@
 // models' flat (no scaling list) intra quantiser for 8-bit video and a 32x32 transform (transformShift = 2):
 //     level = sign(c) * min(32767, (|c| * qScale[qp % 6] + (171 << (qBits - 9))) >> qBits),   qBits = 16 + qp / 6
 //     c'    = clip16((level * (iqScale[qp % 6] << (qp / 6)) + 8) >> 4)
-// PARITY: decision = pinned SATD on the BSV-pinned predictor; transform = pinned; quantiser + inverse: ours (oracle restatement).
+// PARITY: decision = pinned SATD on the BSV-pinned predictor; transform = pinned; quantiser + inverse: ours (no reference artefact exists for them).
 #include "common.cuh"
 #include "kernels.h"
 #include "intra_dev.cuh"
