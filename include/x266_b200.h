@@ -99,7 +99,8 @@ int xGpuSetDctVariant(int variant);
  * host-pointer DCT pipeline | 5 CUDA-core intra decision | 6 accumulate form of the v3 search | 7 first-generation SAD search | 8 CUDA-core SWAR intra interpolation |
  * 9 / 10 / 11 CTAs per SM of the intra / DCT8 / DCT4 persistent grids (0 = shipped) | 12 pageable host buffers: 0 staged through the
  * pinned ring (shipped), 1 handed to the driver, 2 cudaHostRegister per call | 13 host copy threads (0 = X266_HOST_COPY_THREADS or
- * min(8, cpus/2)) | 14 non-temporal staging copies (1 = shipped) | 15 device-side mode[] range check in the *Dev intra entry points. */
+ * min(8, cpus/2)) | 14 non-temporal staging copies (1 = shipped) | 15 device-side mode[] range check in the *Dev intra entry points |
+ * 16 intra32_kernel instantiation (prefetch depth, early table load, CTAs/SM). */
 int xGpuTune(int key, int value);
 
 /* 2-D forward 32x32 transform of nBlocks contiguous row-major int16 blocks:
@@ -159,6 +160,12 @@ int xSad8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t st
  * angular); pred[i] = 32x32 u8 row-major. */
 int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n);
 int xIntra32PredDev(const uint8_t* dRefs, const uint8_t* dMode, uint8_t* dPred, size_t n, void* stream);
+
+/* Mode-major form: for each of nBlocks blocks, the predictions of EVERY mode whose bit is set in modeMask (bit m = mode m, m in 0..34),
+ * in ascending mode order: pred[b][j] = 32x32 u8, j-th set bit.  The block's 129 reference bytes are loaded and staged once for all its
+ * modes (what a rate-distortion search asks for; xIntra32Decide is the fused form that never writes the predictions). */
+int xIntra32PredModes(const uint8_t* refs, size_t nBlocks, uint64_t modeMask, uint8_t* pred);
+int xIntra32PredModesDev(const uint8_t* dRefs, size_t nBlocks, uint64_t modeMask, uint8_t* dPred, void* stream);
 
 /* Fused intra mode decision ("next" row N1; the RTL's Decide channel, src/mkIntra32-wip.bsv:39-48): for each of n
  * 32x32 blocks (cur[i] = 32x32 u8 row-major, refs[i] as for xIntra32Pred) and each mode m in 0..34,

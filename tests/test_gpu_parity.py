@@ -331,6 +331,50 @@ def test_intra32_all_modes(x266, orc, swar):
 
 
 # ------------------------------------------------------------------------- device-pointer entry
+@pytest.mark.parametrize("variant", list(range(5)))
+def test_intra32_kernel_instantiations(x266, orc, variant):
+    """every (prefetch depth, early table load, CTAs/SM) instantiation of the predictor, all 35 modes, ragged count"""
+    rng = np.random.default_rng(variant)
+    n = 35 * 3 + 4
+    refs = rng.integers(0, 256, (n, 129), dtype=np.uint8)
+    refs[-2] = 255; refs[-1] = 0
+    modes = (np.arange(n) % 35).astype(np.uint8)
+    x266.tune(16, variant)
+    try:
+        pred = x266.xIntra32Pred(refs, modes)
+    finally:
+        x266.tune(16, 0)
+    for i in range(n):
+        assert np.array_equal(pred[i], orc.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))), (variant, i, int(modes[i]))
+
+
+def test_intra32_pred_modes(x266, orc):
+    """mode-major entry: all 35 modes of every block, a sparse mask, a single mode, odd block counts, misaligned device refs"""
+    import torch
+    rng = np.random.default_rng(77)
+    for nb, mask in ((1, (1 << 35) - 1), (9, (1 << 35) - 1), (8, 0b1000000000100000000010000000111), (3, 1 << 34), (5, 1 << 0)):
+        refs = rng.integers(0, 256, (nb, 129), dtype=np.uint8)
+        got = x266.xIntra32PredModes(refs, mask)
+        ms = [m for m in range(35) if mask >> m & 1]
+        assert got.shape == (nb, len(ms), 32, 32)
+        for b in range(nb):
+            for j, m in enumerate(ms):
+                assert np.array_equal(got[b, j], orc.intra32(refs[b, :64], refs[b, 64:], m)), (nb, b, m)
+    refs = rng.integers(0, 256, (4, 129), dtype=np.uint8)
+    buf = torch.zeros(4 * 129 + 8, dtype=torch.uint8, device="cuda")
+    out = torch.empty((4, 35, 1024), dtype=torch.uint8, device="cuda")
+    for off in (1, 2, 3):
+        buf[off:off + 4 * 129] = torch.from_numpy(refs.ravel()).cuda()
+        x266.xIntra32PredModesDev(buf.data_ptr() + off, 4, (1 << 35) - 1, out.data_ptr())
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().reshape(4, 35, 32, 32)
+        for b in range(4):
+            for m in range(35):
+                assert np.array_equal(got[b, m], orc.intra32(refs[b, :64], refs[b, 64:], m)), (off, b, m)
+    with pytest.raises(x266.X266Error):
+        x266.xIntra32PredModes(refs, 1 << 35)
+
+
 def test_device_pointer_entry_points(x266, orc):
     import torch
     dev = torch.device("cuda:0")

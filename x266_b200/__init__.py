@@ -13,7 +13,7 @@ from .binding import (  # noqa: F401
     xDct32BatchDev, xDctNBatchDev, xSatd8x8BatchDev, xSatd8x8SearchDev, xIntra32PredDev, xPartialButterfly32Dev,
     xFrameResiDct32, xFrameResiDct32Dev, xConvInputFmtDev, xConvOutput420Dev,
     xTranspose32x32Batch, xTranspose32x32BatchDev,
-    xIntra32Decide, xIntra32DecideDev, xIntra32EncodeBlock, xIntra32EncodeBlockDev, xIntra32Recon, xIntra32ReconDev, xQuantDequantDev, xIdct32Batch, xIdct32BatchDev, xDct32BatchMultiGpu,
+    xIntra32Decide, xIntra32DecideDev, xIntra32PredModes, xIntra32PredModesDev, xIntra32EncodeBlock, xIntra32EncodeBlockDev, xIntra32Recon, xIntra32ReconDev, xQuantDequantDev, xIdct32Batch, xIdct32BatchDev, xDct32BatchMultiGpu,
     sad, xSad8x8Search, xSad8x8SearchDev, xIntra32MmaTable,
     bdpi_dct_block, bdpi_satd_block, X266Error,
 )

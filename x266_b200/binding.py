@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libx266_b200.so")
+LIB_PATH = os.environ.get("X266_B200_LIB", os.path.join(HERE, "libx266_b200.so"))       # override: A/B runs against another build
 
 DCT_AUTO, DCT_BFLY, DCT_IMMA = 0, 1, 2
 
@@ -31,6 +31,15 @@ def build(verbose=False):
 _lib = None
 
 
+def _set(L, name, attr, value):
+    """prototype of one entry point; a missing symbol is an error unless an older build was loaded on purpose (X266_B200_LIB)"""
+    try:
+        setattr(getattr(L, name), attr, value)
+    except AttributeError:
+        if "X266_B200_LIB" not in os.environ:
+            raise
+
+
 def lib():
     """Load the CUDA library.  Raises if it has not been built -- no fallback of any kind."""
     global _lib
@@ -41,51 +50,53 @@ def lib():
                         "(the x266_b200 hot path has no CPU fallback)")
     L = C.CDLL(LIB_PATH)
     vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
-    L.xGpuInit.argtypes = [i]
-    L.xGpuLastError.restype = C.c_char_p
-    L.xGpuKernelLaunches.restype = C.c_ulonglong
-    L.xGpuSetDctVariant.argtypes = [i]
-    L.xGpuTune.argtypes = [i, i]
-    L.xGpuHostRegister.argtypes = [vp, sz]
-    L.xGpuHostUnregister.argtypes = [vp]
-    L.xIntra32MmaTable.argtypes = [vp]
-    L.xDct32Batch.argtypes = [vp, vp, sz, i, i]
-    L.xDct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
-    L.xDct32BatchMultiGpu.argtypes = [vp, vp, sz, i, i, i]
-    L.xIdct32Batch.argtypes = [vp, vp, sz, i, i]
-    L.xIdct32BatchDev.argtypes = [vp, vp, sz, i, i, vp]
-    L.xDctNBatch.argtypes = [i, vp, vp, sz, i, i]
-    L.xDctNBatchDev.argtypes = [i, vp, vp, sz, i, i, vp]
-    L.xPartialButterfly32Dev.argtypes = [vp, vp, i, i, vp]
-    L.xSatd8x8Batch.argtypes = [vp, vp, sz]
-    L.xSatd8x8BatchDev.argtypes = [vp, vp, sz, vp]
-    L.xSatd8x8Search.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp]
-    L.xSatd8x8SearchDev.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp]
-    L.xIntra32Pred.argtypes = [vp, vp, vp, sz]
-    L.xIntra32PredDev.argtypes = [vp, vp, vp, sz, vp]
-    L.xConvInputFmtDev.argtypes = [vp, vp, vp, vp, C.c_ssize_t, i, i, vp]
-    L.xConvOutput420Dev.argtypes = [vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, i, i, vp]
-    L.xFrameResiDct32.argtypes = [vp, vp, i, i, vp, i, i]
-    L.xFrameResiDct32Dev.argtypes = [vp, vp, i, i, vp, i, i, vp]
-    L.xIntra32Decide.argtypes = [vp, vp, vp, vp, sz]
-    L.xIntra32DecideDev.argtypes = [vp, vp, vp, vp, sz, vp]
-    L.xIntra32EncodeBlock.argtypes = [vp, vp, sz, i, vp, vp, vp, vp]
-    L.xIntra32EncodeBlockDev.argtypes = [vp, vp, sz, i, vp, vp, vp, vp, vp]
-    L.xIntra32Recon.argtypes = [vp, vp, vp, sz, i, vp, vp]
-    L.xIntra32ReconDev.argtypes = [vp, vp, vp, sz, i, vp, vp, vp]
-    L.xQuantDequantDev.argtypes = [vp, vp, vp, sz, i, vp]
-    L.xTranspose32x32Batch.argtypes = [vp, vp, sz]
-    L.xTranspose32x32BatchDev.argtypes = [vp, vp, sz, vp]
-    L.sad.argtypes = [vp, vp, sz]
-    L.sad.restype = i
-    L.xSad8x8Search.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp]
-    L.xSad8x8SearchDev.argtypes = [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp]
-    L.partialButterfly32.argtypes = [vp, vp, i, i]
-    L.partialButterfly32.restype = None
-    L.satd8x8.argtypes = [vp]
-    L.satd8x8.restype = i
-    L.dct32_getDct.restype = C.c_ulonglong
-    L.satd8x8_getSatd.restype = C.c_uint
+    _set(L, "xGpuInit", "argtypes", [i])
+    _set(L, "xGpuLastError", "restype", C.c_char_p)
+    _set(L, "xGpuKernelLaunches", "restype", C.c_ulonglong)
+    _set(L, "xGpuSetDctVariant", "argtypes", [i])
+    _set(L, "xGpuTune", "argtypes", [i, i])
+    _set(L, "xGpuHostRegister", "argtypes", [vp, sz])
+    _set(L, "xGpuHostUnregister", "argtypes", [vp])
+    _set(L, "xIntra32MmaTable", "argtypes", [vp])
+    _set(L, "xDct32Batch", "argtypes", [vp, vp, sz, i, i])
+    _set(L, "xDct32BatchDev", "argtypes", [vp, vp, sz, i, i, vp])
+    _set(L, "xDct32BatchMultiGpu", "argtypes", [vp, vp, sz, i, i, i])
+    _set(L, "xIdct32Batch", "argtypes", [vp, vp, sz, i, i])
+    _set(L, "xIdct32BatchDev", "argtypes", [vp, vp, sz, i, i, vp])
+    _set(L, "xDctNBatch", "argtypes", [i, vp, vp, sz, i, i])
+    _set(L, "xDctNBatchDev", "argtypes", [i, vp, vp, sz, i, i, vp])
+    _set(L, "xPartialButterfly32Dev", "argtypes", [vp, vp, i, i, vp])
+    _set(L, "xSatd8x8Batch", "argtypes", [vp, vp, sz])
+    _set(L, "xSatd8x8BatchDev", "argtypes", [vp, vp, sz, vp])
+    _set(L, "xSatd8x8Search", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp])
+    _set(L, "xSatd8x8SearchDev", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp])
+    _set(L, "xIntra32Pred", "argtypes", [vp, vp, vp, sz])
+    _set(L, "xIntra32PredDev", "argtypes", [vp, vp, vp, sz, vp])
+    _set(L, "xConvInputFmtDev", "argtypes", [vp, vp, vp, vp, C.c_ssize_t, i, i, vp])
+    _set(L, "xConvOutput420Dev", "argtypes", [vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, i, i, vp])
+    _set(L, "xFrameResiDct32", "argtypes", [vp, vp, i, i, vp, i, i])
+    _set(L, "xFrameResiDct32Dev", "argtypes", [vp, vp, i, i, vp, i, i, vp])
+    _set(L, "xIntra32Decide", "argtypes", [vp, vp, vp, vp, sz])
+    _set(L, "xIntra32DecideDev", "argtypes", [vp, vp, vp, vp, sz, vp])
+    _set(L, "xIntra32PredModes", "argtypes", [vp, sz, C.c_uint64, vp])
+    _set(L, "xIntra32PredModesDev", "argtypes", [vp, sz, C.c_uint64, vp, vp])
+    _set(L, "xIntra32EncodeBlock", "argtypes", [vp, vp, sz, i, vp, vp, vp, vp])
+    _set(L, "xIntra32EncodeBlockDev", "argtypes", [vp, vp, sz, i, vp, vp, vp, vp, vp])
+    _set(L, "xIntra32Recon", "argtypes", [vp, vp, vp, sz, i, vp, vp])
+    _set(L, "xIntra32ReconDev", "argtypes", [vp, vp, vp, sz, i, vp, vp, vp])
+    _set(L, "xQuantDequantDev", "argtypes", [vp, vp, vp, sz, i, vp])
+    _set(L, "xTranspose32x32Batch", "argtypes", [vp, vp, sz])
+    _set(L, "xTranspose32x32BatchDev", "argtypes", [vp, vp, sz, vp])
+    _set(L, "sad", "argtypes", [vp, vp, sz])
+    _set(L, "sad", "restype", i)
+    _set(L, "xSad8x8Search", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp])
+    _set(L, "xSad8x8SearchDev", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp])
+    _set(L, "partialButterfly32", "argtypes", [vp, vp, i, i])
+    _set(L, "partialButterfly32", "restype", None)
+    _set(L, "satd8x8", "argtypes", [vp])
+    _set(L, "satd8x8", "restype", i)
+    _set(L, "dct32_getDct", "restype", C.c_ulonglong)
+    _set(L, "satd8x8_getSatd", "restype", C.c_uint)
     _lib = L
     return L
 
@@ -238,6 +249,19 @@ def xIntra32Decide(cur, refs):
     best = np.empty(cur.shape[0], np.int32)
     _ck(lib().xIntra32Decide(cur.ctypes.data, refs.ctypes.data, cost.ctypes.data, best.ctypes.data, cur.shape[0]), "xIntra32Decide")
     return cost, best
+
+
+def xIntra32PredModes(refs, mode_mask=(1 << 35) - 1):
+    """every mode of mode_mask for every block: [nBlocks][popcount(mask)][32][32]"""
+    refs = _np(refs, np.uint8).reshape(-1, 129)
+    nm = bin(mode_mask).count("1")
+    pred = np.empty((refs.shape[0], nm, 32, 32), np.uint8)
+    _ck(lib().xIntra32PredModes(refs.ctypes.data, refs.shape[0], mode_mask, pred.ctypes.data), "xIntra32PredModes")
+    return pred
+
+
+def xIntra32PredModesDev(d_refs, n_blocks, mode_mask, d_pred, stream=0):
+    _ck(lib().xIntra32PredModesDev(d_refs, n_blocks, mode_mask, d_pred, stream), "xIntra32PredModesDev")
 
 
 def xIntra32EncodeBlock(cur, refs, qp, want_cost=True):

@@ -551,6 +551,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 13 && value >= 0) { set_host_copy_threads(value); return 0; }
     if (key == 14) { set_host_copy_nt(value); return 0; }
     if (key == 15) { g_checkModes.store(value ? 1 : 0); return 0; }
+    if (key == 16) { set_intra_variant(value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }
 
@@ -836,6 +837,27 @@ extern "C" int xIntra32Pred(const uint8_t* refs, const uint8_t* mode, uint8_t* p
     return run_chunked(ins, 2, &out, 1, n, (size_t)1 << 15,
                        [&](void* const* dI, void* const* dO, size_t, size_t np, cudaStream_t st) {
                            return launch_intra32((const uint8_t*)dI[0], (const uint8_t*)dI[1], (uint8_t*)dO[0], np, st);
+                       });
+}
+
+extern "C" int xIntra32PredModesDev(const uint8_t* dRefs, size_t nBlocks, uint64_t modeMask, uint8_t* dPred, void* stream)
+{
+    if ((modeMask >> 35) || (nBlocks && modeMask && (!dRefs || !dPred))) return fail("xIntra32PredModesDev", cudaSuccess);
+    if (reinterpret_cast<uintptr_t>(dPred) & 15) return fail("xIntra32PredModesDev: 16-byte alignment of pred", cudaSuccess);
+    if (dev_ready()) return -1;
+    CK(launch_intra32_modes(dRefs, modeMask, dPred, nBlocks, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int xIntra32PredModes(const uint8_t* refs, size_t nBlocks, uint64_t modeMask, uint8_t* pred)
+{
+    if ((modeMask >> 35) || (nBlocks && modeMask && (!refs || !pred))) return fail("xIntra32PredModes", cudaSuccess);
+    const size_t nModes = (size_t)__builtin_popcountll(modeMask);
+    if (nBlocks == 0 || nModes == 0) return 0;
+    const HostArr in{ const_cast<uint8_t*>(refs), 129 }, out{ pred, nModes * 1024 };
+    return run_chunked(&in, 1, &out, 1, nBlocks, ((size_t)1 << 15) / nModes + 1,
+                       [&](void* const* dI, void* const* dO, size_t, size_t nb, cudaStream_t st) {
+                           return launch_intra32_modes((const uint8_t*)dI[0], modeMask, (uint8_t*)dO[0], nb, st);
                        });
 }
 
