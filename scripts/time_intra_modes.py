@@ -44,14 +44,6 @@ for v in sys.argv[1:]:
     xb.tune(int(k), int(val))
     show(f"tune {k}={val}: i % 35", inter)
     xb.tune(int(k), 0)
-names = {0: "depth 1, late table, 5 CTAs", 1: "depth 2, late table, 5", 2: "depth 1, early table, 5", 3: "depth 2, late table, 4",
-         4: "depth 1, late table, 6"}
-for var in range(5):
-    xb.tune(16, var)
-    show(f"variant {var} ({names[var]}): i%35", inter)
-    show(f"variant {var}: all mode 26", torch.full((n,), 26, device="cuda", dtype=torch.uint8))
-    show(f"variant {var}: all mode 30", torch.full((n,), 30, device="cuda", dtype=torch.uint8))
-xb.tune(16, 0)
 # mode-major entry: all 35 modes of 29960 blocks = 1 048 600 predictions
 nb = n // 35 + 1
 big = torch.empty((nb, 35, 1024), device="cuda", dtype=torch.uint8)

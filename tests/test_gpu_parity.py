@@ -331,23 +331,6 @@ def test_intra32_all_modes(x266, orc, swar):
 
 
 # ------------------------------------------------------------------------- device-pointer entry
-@pytest.mark.parametrize("variant", list(range(5)))
-def test_intra32_kernel_instantiations(x266, orc, variant):
-    """every (prefetch depth, early table load, CTAs/SM) instantiation of the predictor, all 35 modes, ragged count"""
-    rng = np.random.default_rng(variant)
-    n = 35 * 3 + 4
-    refs = rng.integers(0, 256, (n, 129), dtype=np.uint8)
-    refs[-2] = 255; refs[-1] = 0
-    modes = (np.arange(n) % 35).astype(np.uint8)
-    x266.tune(16, variant)
-    try:
-        pred = x266.xIntra32Pred(refs, modes)
-    finally:
-        x266.tune(16, 0)
-    for i in range(n):
-        assert np.array_equal(pred[i], orc.intra32(refs[i, :64], refs[i, 64:], int(modes[i]))), (variant, i, int(modes[i]))
-
-
 def test_intra32_pred_modes(x266, orc):
     """mode-major entry: all 35 modes of every block, a sparse mask, a single mode, odd block counts, misaligned device refs"""
     import torch

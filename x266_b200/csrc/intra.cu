@@ -27,11 +27,6 @@ namespace x266 {
 // instead of 512 two-pixel multiply-adds; the accumulators leave through a per-warp tile as byte pairs (one PRMT each) and
 // are stored with the same two 512-byte instructions as before.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_u8u8_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
-}
 
 static const int h_intraAngle[35] = { 0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
                                       -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
@@ -122,7 +117,7 @@ cudaError_t launch_mode_range_check(const uint8_t* mode, size_t n, int maxMode, 
     return cudaGetLastError();
 }
 
-static const uint32_t* intra_mma_table_dev(cudaError_t* err)
+const uint32_t* intra_mma_table_dev(cudaError_t* err)
 {
     int dev = 0;
     *err = cudaGetDevice(&dev);
@@ -341,16 +336,19 @@ __device__ __forceinline__ void intra_generate(int mode, uint8_t* __restrict__ s
     }
 }
 
-// DEPTH = predictions in flight ahead of the one being generated (1 or 2); EARLYTAB = the fragment-table row of a fractional mode
-// is requested before the staging instead of right in front of the MMAs; MINB = CTAs per SM the register allocation must allow.
-template <bool ALIGNED, int DEPTH, bool EARLYTAB, int MINB, bool MMA>
-__global__ void __launch_bounds__(INTRA_WARPS * 32, MINB)
+// The generic predictor: one warp per prediction, modes in the caller's order.  This kernel is kept as ONE monolithic body on purpose: ptxas's
+// schedule of it is fragile -- the same code routed through intra_generate() above, or with the two-line change that stores modes 2 / 10
+// without the transpose, lands on a different register allocation (4 CTAs per SM, or 5 with the MMA section serialised) and loses 4-5 % on
+// the 30 fractional modes (A/B on one box: 0.762 of the HBM roofline as below, 0.725 refactored; profiles/r02_intra_experiments.md).
+// intra_generate() carries the improved whole-sample / planar paths and serves the mode-major kernel.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(INTRA_WARPS * 32)
 intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ modes, uint8_t* __restrict__ pred, size_t n,
-               const uint32_t* __restrict__ mmaTab)
+               const uint32_t* __restrict__ mmaTab, int useMma)
 {
     __shared__ __align__(16) uint8_t strip[INTRA_WARPS][INTRA_STRIP + 16];
     __shared__ __align__(16) uint8_t raw[INTRA_WARPS][144];      // left[64] | top[65]
-    __shared__ __align__(16) uint8_t tile[INTRA_WARPS][MMA ? 16 : 32 * 36]; // output tile of the tensor-core path (pitch 48) / transpose tile (pitch 36)
+    __shared__ __align__(16) uint8_t tile[INTRA_WARPS][32 * 48]; // output tile of the tensor-core path (pitch 48) / transpose tile (pitch 36)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* sraw = raw[warp];
     uint32_t* strip32 = reinterpret_cast<uint32_t*>(strip[warp]);
@@ -364,13 +362,9 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
     const uint32_t nLast = (uint32_t)n - 1;                          // n < 2^32: a prediction is 1 KiB of output
     uint32_t p = blockIdx.x * INTRA_WARPS + warp;                    // prediction being generated
     if (p > nLast) return;
-    // two predictions ahead: at 40 warps per SM one warp iteration lasts about as long as a loaded DRAM access, so a single
-    // prefetch in flight leaves the copy modes latency bound (measured: 0.90 of the roofline with one)
-    struct Pre { uint32_t w0, w1; int a, mode; };
-    Pre pre[2] = { { 0, 0, 0, 1 }, { 0, 0, 0, 1 } };
-    auto prefetch = [&](uint32_t q, Pre& pf) {
-        uint32_t nw0 = 0, nw1 = 0;
-        int na = 0;
+    uint32_t nw0 = 0, nw1 = 0;
+    int na = 0, nmode = 1;
+    auto prefetch = [&](uint32_t q) {
         const uint8_t* src = refs + (size_t)q * 129;
         if (ALIGNED) {
             na = (int)(reinterpret_cast<uintptr_t>(src) & 3);
@@ -388,20 +382,12 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
             nw0 = src[4 * lane] | (src[4 * lane + 1] << 8) | (src[4 * lane + 2] << 16) | ((uint32_t)src[4 * lane + 3] << 24);
             if (lane == 0) nw1 = src[128];
         }
-        pf.w0 = nw0; pf.w1 = nw1; pf.a = na; pf.mode = modes[q];
+        nmode = modes[q];
     };
-    prefetch(p, pre[0]);
-    if (DEPTH == 2 && p + pstride <= nLast && p + pstride >= p) prefetch(p + pstride, pre[1]);
+    prefetch(p);
 
     for (; p <= nLast; p += pstride) {
-        const uint32_t nw0 = pre[0].w0, nw1 = pre[0].w1;
-        const int na = pre[0].a;
-        const int mode = pre[0].mode > 34 ? 1 : pre[0].mode;     // host API rejects > 34; keep device reads in range
-        if (DEPTH == 2) pre[0] = pre[1];
-        const bool frac = MMA && mode >= 2 && (c_intraAngle[mode] & 31) != 0;
-        uint4 T0 = make_uint4(0, 0, 0, 0), T1 = T0;              // fragment-table row of a fractional mode
-        const uint4* tp = reinterpret_cast<const uint4*>(mmaTab) + mode * 64 + lane;
-        if (EARLYTAB && frac) { T0 = __ldg(tp); T1 = __ldg(tp + 32); }
+        const int mode = nmode > 34 ? 1 : nmode;                 // host API rejects > 34; keep device reads in range
         uint32_t R, last;                                        // R = raw[4*lane .. 4*lane+3], last = raw[128]
         {
             uint32_t up = __shfl_down_sync(0xffffffffu, nw0, 1);
@@ -415,20 +401,152 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
             if (lane == 0) sraw[128] = (uint8_t)last;
         }
         uint32_t* out = reinterpret_cast<uint32_t*>(pred + (size_t)p * 1024);
-        if ((uint64_t)p + (uint64_t)DEPTH * pstride <= nLast) prefetch(p + DEPTH * pstride, pre[DEPTH - 1]);
+        if (p + pstride <= nLast) prefetch(p + pstride);
+        const uint8_t* left = sraw;          // left[i] = pixel (-1, i)
+        const uint8_t* top = sraw + 64;      // top[0] = corner, top[1+i] = pixel (i, -1)
+        const bool isVer = mode >= 18;
+        const int ang = c_intraAngle[mode];
+
         if (mode >= 2) {
             // reference line ref[-32..65] in the strip, ref[0] at byte ref0: vertical modes ref[i] = top[i] = raw[64+i]
             // (word aligned at 36), horizontal modes ref[0] = corner, ref[1+j] = left[j] = raw[j] (ref[1] word aligned at 36)
             // -- so the main part is one 32-bit store per lane straight from the registers.
-            if (mode >= 18) {
+            const int ref0 = isVer ? 36 : 35;
+            uint8_t* sref = strip[warp] + ref0;
+            if (isVer) {
                 if (lane >= 16) strip32[9 + lane - 16] = R;
-                if (lane == 0) strip[warp][36 + 64] = (uint8_t)last;
+                if (lane == 0) sref[64] = (uint8_t)last;
             } else {
                 if (lane < 16) strip32[9 + lane] = R;
-                if (lane == 16) strip[warp][35] = (uint8_t)R;
+                if (lane == 16) sref[0] = (uint8_t)R;
+            }
+            if (ang < 0) {
+                __syncwarp();                                     // sraw complete
+                const int inv = c_intraInvMode[mode];
+                const int k = lane + 1;                           // projects ref[-k], k = 1..32
+                if (-k >= ang) {
+                    const int s = (k * inv + 128) >> 8;
+                    sref[-k] = isVer ? left[s - 1] : top[s];
+                }
+            }
+            __syncwarp();
+            if (useMma && (ang & 31) != 0) {
+                // ---- tensor-core path (see the comment above mma_u8u8_16832)
+                const int g4 = lane >> 2, q4 = lane & 3;
+                const int base = ang >= 0 ? (ang >> 5) + 1 : ang + 1;
+                const uint32_t keep = q4 == 3 ? 0x00FFFFFFu : 0xFFFFFFFFu, one = q4 == 3 ? 0x01000000u : 0u;   // Hankel row k = 31 := 1
+                const uint4* tp = reinterpret_cast<const uint4*>(mmaTab) + mode * 64 + lane;
+                const uint4 T0 = __ldg(tp), T1 = __ldg(tp + 32);
+                uint8_t* orow = reinterpret_cast<uint8_t*>(out) + g4 * 32 + 8 * q4;      // row g, pixels 8q..8q+7
+                // pixel = byte 1 of each sum: four sums -> one word
+                auto word = [](const int (&a)[4], const int (&b)[4], int r) {
+                    return __byte_perm(__byte_perm((uint32_t)a[2 * r], (uint32_t)a[2 * r + 1], 0x5151),
+                                       __byte_perm((uint32_t)b[2 * r], (uint32_t)b[2 * r + 1], 0x5151), 0x5410);
+                };
+                if (isVer) {
+                    // B = Hankel windows with permuted columns: column n = g of tile t is pixel 8(g>>1) + 2t + (g&1)
+                    const int cb = ref0 + base + 4 * q4 + 8 * (g4 >> 1) + (g4 & 1);
+                    const uint32_t* wp = strip32 + (cb >> 2);
+                    const int sh = (cb & 3) * 8;
+                    uint32_t wl[4], wh[4];                                   // windows at byte offsets 2t and 16 + 2t
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const uint32_t xa = wp[4 * j], xb = wp[4 * j + 1], xc = wp[4 * j + 2], xd = wp[4 * j + 3];
+                        const uint32_t lo = __funnelshift_r(xa, xb, sh), mid = __funnelshift_r(xb, xc, sh), hi = __funnelshift_r(xc, xd, sh);
+                        uint32_t* w = j ? wh : wl;
+                        w[0] = lo; w[1] = __byte_perm(lo, mid, 0x5432); w[2] = mid; w[3] = __byte_perm(mid, hi, 0x5432);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++) wh[t] = (wh[t] & keep) | one;
+#pragma unroll
+                    for (int m = 0; m < 2; m++) {
+                        const uint4 A = m ? T1 : T0;
+                        int d[4][4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) mma_u8u8_16832(d[t], A.x, A.y, A.z, A.w, wl[t], wh[t]);
+                        *reinterpret_cast<uint2*>(orow + (16 * m) * 32) = make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0));
+                        *reinterpret_cast<uint2*>(orow + (16 * m + 8) * 32) = make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1));
+                    }
+                } else {
+                    // A = Hankel windows of the left reference (rows y = 16m + g, g + 8), B = W^T from the table
+                    const int ca = ref0 + base + 4 * q4 + g4;
+                    const uint32_t* wp = strip32 + (ca >> 2);
+                    const int sh = (ca & 3) * 8;
+                    uint32_t win[6];
+#pragma unroll
+                    for (int j = 0; j < 6; j++) win[j] = __funnelshift_r(wp[2 * j], wp[2 * j + 1], sh);
+                    uint32_t wpat[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) wpat[j] = (win[j + 2] & keep) | one;
+#pragma unroll
+                    for (int m = 0; m < 2; m++) {
+                        int d[4][4];
+                        mma_u8u8_16832(d[0], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T0.x, T0.y);
+                        mma_u8u8_16832(d[1], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T0.z, T0.w);
+                        mma_u8u8_16832(d[2], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T1.x, T1.y);
+                        mma_u8u8_16832(d[3], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T1.z, T1.w);
+                        *reinterpret_cast<uint2*>(orow + (16 * m) * 32) = make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0));
+                        *reinterpret_cast<uint2*>(orow + (16 * m + 8) * 32) = make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1));
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            uint32_t w[2][4];
+            intra_angular_rows(strip32, ref0, ang, lane, w);
+            if (isVer) {
+#pragma unroll
+                for (int it = 0; it < 2; it++)
+                    reinterpret_cast<uint4*>(out)[it * 32 + lane] = make_uint4(w[it][0], w[it][1], w[it][2], w[it][3]);
+            } else {
+#pragma unroll
+                for (int it = 0; it < 2; it++) {
+                    uint32_t* trow = reinterpret_cast<uint32_t*>(&tile[warp][(16 * it + (lane >> 1)) * 36 + 16 * (lane & 1)]);
+                    trow[0] = w[it][0]; trow[1] = w[it][1]; trow[2] = w[it][2]; trow[3] = w[it][3];
+                }
+                __syncwarp();
+                // lane <-> output rows r0..r0+3, columns c0..c0+7: two 4x4 byte blocks of P_v^T
+                const int r0 = 4 * (lane >> 2), c0 = 8 * (lane & 3);
+                uint32_t W[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) W[k] = *reinterpret_cast<const uint32_t*>(&tile[warp][(c0 + k) * 36 + r0]);
+                uint32_t o8[4][2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t t0 = __byte_perm(W[4 * h], W[4 * h + 1], 0x5140), t1 = __byte_perm(W[4 * h + 2], W[4 * h + 3], 0x5140);
+                    const uint32_t t2 = __byte_perm(W[4 * h], W[4 * h + 1], 0x7362), t3 = __byte_perm(W[4 * h + 2], W[4 * h + 3], 0x7362);
+                    o8[0][h] = __byte_perm(t0, t1, 0x5410); o8[1][h] = __byte_perm(t0, t1, 0x7632);
+                    o8[2][h] = __byte_perm(t2, t3, 0x5410); o8[3][h] = __byte_perm(t2, t3, 0x7632);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(out) + (r0 + i) * 32 + c0) = make_uint2(o8[i][0], o8[i][1]);
+            }
+        } else if (mode == 1) {
+            __syncwarp();
+            int s = left[lane] + top[1 + lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const uint32_t dc = (uint32_t)((s + 32) >> 6) * 0x01010101u;
+#pragma unroll
+            for (int it = 0; it < 8; it++) out[it * 32 + lane] = dc;
+        } else {
+            __syncwarp();
+            const int rsub = lane >> 3, c0 = (lane & 7) * 4;
+            const int tr = top[33], bl = left[32];
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int row = 4 * it + rsub;
+                uint32_t packed = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int col = c0 + j;
+                    const int v = ((31 - col) * left[row] + (col + 1) * tr + (31 - row) * top[1 + col] + (row + 1) * bl + 32) >> 6;
+                    packed |= (uint32_t)v << (8 * j);
+                }
+                out[it * 32 + lane] = packed;
             }
         }
-        intra_generate<EARLYTAB, MMA>(mode, strip[warp], sraw, tile[warp], out, tp, T0, T1, lane);
         __syncwarp();
     }
 }
@@ -706,40 +824,23 @@ cudaError_t launch_intra32_modes(const uint8_t* refs, unsigned long long modeMas
                     : launch_intra32_modes_as<false, true>(refs, modeMask, nModes, pred, nBlocks, tab, st);
 }
 
-static std::atomic<int> g_intraVariant{0};  // tuning/diagnostic: (depth, early table, CTAs/SM) instantiation, see launch_intra32
-void set_intra_variant(int v) { g_intraVariant = v; }
-
-template <bool ALIGNED, int DEPTH, bool EARLYTAB, int MINB, bool MMA>
-static cudaError_t launch_intra32_as(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, const uint32_t* tab, cudaStream_t st)
-{
-    const void* kern = (const void*)intra32_kernel<ALIGNED, DEPTH, EARLYTAB, MINB, MMA>;
-    const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
-    const int perSm = g_intraCtas > 0 ? g_intraCtas.load() : resident_ctas_per_sm(kern, INTRA_WARPS * 32, 0);
-    const size_t cap = (size_t)sm_count() * perSm;
-    intra32_kernel<ALIGNED, DEPTH, EARLYTAB, MINB, MMA><<<(unsigned)(want < cap ? want : cap), INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n, tab);
-    count_launch();
-    return cudaGetLastError();
-}
-
 cudaError_t launch_intra32(const uint8_t* refs, const uint8_t* mode, uint8_t* pred, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     if (n > ((size_t)1 << 31)) return cudaErrorInvalidValue;          // 32-bit prediction index in the kernel (2 TiB of output)
+    const size_t want = (n + INTRA_WARPS - 1) / INTRA_WARPS;
+    const bool aligned4 = (reinterpret_cast<uintptr_t>(refs) & 3) == 0;
+    const int perSm = g_intraCtas > 0 ? g_intraCtas.load()
+                                      : resident_ctas_per_sm(aligned4 ? (const void*)intra32_kernel<true> : (const void*)intra32_kernel<false>, INTRA_WARPS * 32, 0);
+    const size_t cap = (size_t)sm_count() * perSm;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     cudaError_t e;
     const uint32_t* tab = intra_mma_table_dev(&e);
     if (!tab) return e;
-    const bool aligned4 = (reinterpret_cast<uintptr_t>(refs) & 3) == 0;
-    if (g_intraSwar) return aligned4 ? launch_intra32_as<true, 1, false, 5, false>(refs, mode, pred, n, tab, st)
-                                     : launch_intra32_as<false, 1, false, 4, false>(refs, mode, pred, n, tab, st);
-    if (!aligned4) return launch_intra32_as<false, 1, false, 4, true>(refs, mode, pred, n, tab, st);
-    switch (g_intraVariant.load()) {
-    default:
-    case 0: return launch_intra32_as<true, 1, false, 5, true>(refs, mode, pred, n, tab, st);
-    case 1: return launch_intra32_as<true, 2, false, 5, true>(refs, mode, pred, n, tab, st);
-    case 2: return launch_intra32_as<true, 1, true, 5, true>(refs, mode, pred, n, tab, st);
-    case 3: return launch_intra32_as<true, 2, false, 4, true>(refs, mode, pred, n, tab, st);
-    case 4: return launch_intra32_as<true, 1, false, 6, true>(refs, mode, pred, n, tab, st);
-    }
+    if (aligned4) intra32_kernel<true><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n, tab, !g_intraSwar);
+    else intra32_kernel<false><<<grid, INTRA_WARPS * 32, 0, st>>>(refs, mode, pred, n, tab, !g_intraSwar);
+    count_launch();
+    return cudaGetLastError();
 }
 
 } // namespace x266

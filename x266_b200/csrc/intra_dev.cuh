@@ -23,6 +23,20 @@ __device__ __forceinline__ uint32_t intra_row4(uint32_t a, uint32_t b, int f)
     return pe | (po << 8);
 }
 
+// D(16x8,s32) += A(16x32,u8,row) * B(32x8,u8,col): the angular / planar predictors' weight x Hankel product
+__device__ __forceinline__ void mma_u8u8_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+// pixel = byte 1 of each 32-bit sum: the four sums of accumulator rows r of two adjacent n8 tiles -> one word of four pixels
+__device__ __forceinline__ uint32_t intra_word(const int (&a)[4], const int (&b)[4], int r)
+{
+    return __byte_perm(__byte_perm((uint32_t)a[2 * r], (uint32_t)a[2 * r + 1], 0x5151),
+                       __byte_perm((uint32_t)b[2 * r], (uint32_t)b[2 * r + 1], 0x5151), 0x5410);
+}
+
 constexpr int INTRA_WARPS = 8;
 constexpr int INTRA_STRIP = 112;            // 32 (negative part) + 66 + padding, multiple of 16
 

@@ -46,7 +46,6 @@ void intra_mma_table_copy(uint32_t* out);   // 35 x 256 words: the per-mode MMA 
 void set_dct8_ctas(int v);        // tuning/diagnostic: CTAs per SM of the dct8 / dct4 persistent grids
 void set_dct4_ctas(int v);
 void set_intra_ctas(int v);       // tuning/diagnostic: CTAs per SM of the intra kernel's persistent grid
-void set_intra_variant(int v);    // tuning/diagnostic: intra32_kernel instantiation (prefetch depth, early table load, CTAs/SM)
 void set_intra_swar(int on);      // tuning/diagnostic: CUDA-core SWAR interpolation instead of the tensor-core angular path
 void set_sad_search_v1(int on);   // tuning/diagnostic: first-generation SAD search (one CTA per block)
 void set_search_acc_form(int f);  // tuning/diagnostic: accumulate form of the v3 search (satd_packed.h maxsum4)
@@ -62,6 +61,7 @@ cudaError_t launch_intra32_recon(const uint8_t* cur, const uint8_t* refs, const 
                                  uint8_t* recon, cudaStream_t st);
 cudaError_t launch_quant_dequant(const int16_t* coef, int16_t* level, int16_t* dq, size_t nCoef, int qp, cudaStream_t st);
 cudaError_t launch_intra32_modes(const uint8_t* refs, unsigned long long modeMask, uint8_t* pred, size_t nBlocks, cudaStream_t st);
+const uint32_t* intra_mma_table_dev(cudaError_t* err);   // device copy of the fragment table on the current device (after intra_device_init)
 cudaError_t intra_device_init();   // uploads the intra fragment table to the current device (called once per device by ffi.cu: ctx_get)
 void intra_device_free();          // releases it (xGpuFree)
 // debug (xGpuTune 15): *bad += number of mode[i] > maxMode
