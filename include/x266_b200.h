@@ -204,12 +204,37 @@ int xIntra32MmaTable(uint32_t* table /* [35 * 256] */);
  * width/16 tiles per row (m_frames_strd, x266.cpp:503); passed here as void* / uint8_t*.
  * ============================================================================================== */
 
+/* src/x266.cpp:55-63: the 512-byte tile of the encoder's frame stores (all members are bytes: no padding, PACKED or not) */
+typedef struct _ref_block_t {
+    uint8_t m_Y[16 * 16];         /* 256 bytes - Y  */
+    uint8_t m_C[2 * 8 * 8];       /* 128 bytes - UV */
+    uint8_t m_I[128];             /* 128 bytes - Info */
+} ref_block_t;
+
+/* replaces src/x266.cpp:415-453 and :455-492 with the reference's own names and signatures (HOST pointers, synchronous, void; the
+ * reference asserts on width / height not being multiples of 16 -- this library prints the error and aborts).  These are the two calls
+ * xEncodeFrame already makes (x266.cpp:537).  m_I is left untouched, chroma stride of xConvInputFmt is strdY >> 1 (:426). */
+void xConvInputFmt(ref_block_t* pBlock, const uint8_t* inpY, const uint8_t* inpU, const uint8_t* inpV, const intptr_t strdY,
+                   const int width, const int height);
+void xConvOutput420(const ref_block_t* pBlock, uint8_t* outY, const intptr_t strdY, uint8_t* outU, uint8_t* outV, intptr_t strdC,
+                    const int width, const int height);
+
 /* replaces src/x266.cpp:415-453 (planar YUV 4:2:0 -> tiles; m_I untouched) on device-resident planes */
 int xConvInputFmtDev(void* dTiles, const uint8_t* dY, const uint8_t* dU, const uint8_t* dV, intptr_t strdY,
                      int width, int height, void* stream);
 /* replaces src/x266.cpp:455-492 (tiles -> planar) */
 int xConvOutput420Dev(const void* dTiles, uint8_t* dY, intptr_t strdY, uint8_t* dU, uint8_t* dV, intptr_t strdC,
                       int width, int height, void* stream);
+
+/* Full search straight on the encoder's frame stores: curTiles / refTiles are ref_block_t frames (m_frames[0] and a reference,
+ * src/x266.cpp:99), width and height multiples of 16; the reference is edge-replicated by `range` pixels inside the call.
+ * Outputs and conventions exactly as xSatd8x8Search / xSad8x8Search. */
+int xSatd8x8SearchTiled(const void* curTiles, const void* refTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                        uint32_t* cost, int32_t* best);
+int xSatd8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                           uint32_t* dCost, int32_t* dBest, void* stream);
+int xSad8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                          uint32_t* dCost, int32_t* dBest, void* stream);
 
 /* Fused residual + transform for the block loop of xEncodeFrame (src/x266.cpp:537-546): for every 32x32 luma
  * block b (raster order, width and height multiples of 32) of the tiled frames cur and pred,

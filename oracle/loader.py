@@ -26,7 +26,8 @@ def build(force=False):
     if need:
         subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so", f"X266_REF={REF_TREE}"])
     ref_so = os.path.join(HERE, "_ref", "libx266ref.so")
-    if os.path.exists(os.path.join(REF_TREE, "src_tb", "dct32.c")) and (force or not os.path.exists(ref_so)):
+    conv_so = os.path.join(HERE, "_ref", "libx266conv.so")
+    if os.path.exists(os.path.join(REF_TREE, "src_tb", "dct32.c")) and (force or not os.path.exists(ref_so) or not os.path.exists(conv_so)):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref", f"X266_REF={REF_TREE}"])
 
 
@@ -221,6 +222,29 @@ class Oracle:
         out = np.empty(n, np.int16)
         self.lib.orc_fill_residual(out, n, seed, kind)
         return out
+
+
+def have_ref_conv():
+    return os.path.exists(os.path.join(HERE, "_ref", "libx266conv.so"))
+
+
+class RefConv:
+    """The unmodified xConvInputFmt / xConvOutput420 of src/x266.cpp:415-492 (oracle/_ref/libx266conv.so, ref_conv_slice.sh)."""
+
+    def __init__(self):
+        build()
+        L = self.lib = C.CDLL(os.path.join(HERE, "_ref", "libx266conv.so"))
+        L.ref_xConvInputFmt.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_ssize_t, C.c_int, C.c_int]
+        L.ref_xConvOutput420.argtypes = [_u8p, _u8p, C.c_ssize_t, _u8p, _u8p, C.c_ssize_t, C.c_int, C.c_int]
+        assert L.ref_sizeof_ref_block_t() == 512
+
+    def input_fmt(self, y_buf, u_buf, v_buf, strd_y, w, h, tiles):
+        """planes as flat byte buffers with luma stride strd_y (chroma stride strd_y >> 1, x266.cpp:426); tiles is written in place"""
+        self.lib.ref_xConvInputFmt(tiles, y_buf, u_buf, v_buf, strd_y, w, h)
+        return tiles
+
+    def output420(self, tiles, y_buf, strd_y, u_buf, v_buf, strd_c, w, h):
+        self.lib.ref_xConvOutput420(tiles, y_buf, strd_y, u_buf, v_buf, strd_c, w, h)
 
 
 class Ref:

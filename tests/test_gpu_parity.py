@@ -456,6 +456,63 @@ def test_conv_input_output_fmt_dev(x266, orc):
     assert np.array_equal(oY.cpu().numpy(), Y) and np.array_equal(oU.cpu().numpy(), U) and np.array_equal(oV.cpu().numpy(), V)
 
 
+def test_host_converters_reference_signatures(x266):
+    """xConvInputFmt / xConvOutput420 with the reference's names and signatures (host pointers) against the COMPILED reference functions
+    (oracle/_ref/libx266conv.so), strided planes, m_I preserved"""
+    from oracle import RefConv, have_ref_conv
+    if not have_ref_conv():
+        pytest.skip("oracle/_ref/libx266conv.so not available")
+    rc = RefConv()
+    rng = np.random.default_rng(3)
+    for w, h, strd in ((16, 16, 16), (176, 144, 200), (1920, 1088, 1920)):
+        Yb = rng.integers(0, 256, strd * h, dtype=np.uint8)
+        Ub = rng.integers(0, 256, (strd >> 1) * (h // 2), dtype=np.uint8)
+        Vb = rng.integers(0, 256, (strd >> 1) * (h // 2), dtype=np.uint8)
+        want = np.full((w // 16) * (h // 16) * 512, 0x5A, np.uint8)
+        got = want.copy()
+        rc.input_fmt(Yb, Ub, Vb, strd, w, h, want)
+        x266.xConvInputFmt(got, Yb, Ub, Vb, strd, w, h)
+        assert np.array_equal(got, want), (w, h, strd)
+        wy = np.full(strd * h, 7, np.uint8); wu = np.full((strd >> 1) * (h // 2), 7, np.uint8); wv = wu.copy()
+        gy, gu, gv = wy.copy(), wu.copy(), wv.copy()
+        rc.output420(want, wy, strd, wu, wv, strd >> 1, w, h)
+        x266.xConvOutput420(got, gy, strd, gu, gv, strd >> 1, w, h)
+        assert np.array_equal(gy, wy) and np.array_equal(gu, wu) and np.array_equal(gv, wv), (w, h, strd)   # bytes past `width` untouched too
+
+
+def test_tiled_search_equals_planar_search(x266, orc):
+    """search on the encoder's own frame stores: ref_block_t frames in, in-call edge replication == planar search on the config-3 frames
+    (1920x1088, the height the encoder pads 1080 to) and on small ragged cases, SATD and SAD"""
+    import torch
+    from search_frames import config3_frames
+    for (w, h, r, full) in ((1920, 1088, 32, True), (48, 32, 8, False), (64, 16, 16, False)):
+        cur, refp = config3_frames(w, h, r) if full else (np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8), None)
+        if refp is None:
+            ref = np.random.default_rng(h).integers(0, 256, (h, w), dtype=np.uint8)
+            refp = np.pad(ref, r, mode="edge")
+        ref = refp[r:r + h, r:r + w]
+        zc = np.zeros((h // 2, w // 2), np.uint8)
+        ct, rt = orc.conv_input_fmt(cur, zc, zc), orc.conv_input_fmt(np.ascontiguousarray(ref), zc, zc)
+        nb = (w // 8) * (h // 8)
+        if full:
+            _, wb = x266.xSatd8x8Search(cur, refp, r, want_cost=False)
+            _, gb = x266.xSatd8x8SearchTiled(ct, rt, w, h, r, want_cost=False)
+            assert np.array_equal(gb, wb)
+            sub = (1000, 1300)
+            wc, _ = x266.xSatd8x8Search(cur, refp, r, *sub, want_best=False)
+            gc, _ = x266.xSatd8x8SearchTiled(ct, rt, w, h, r, *sub, want_best=False)
+            assert np.array_equal(gc, wc)
+        else:
+            wc, wb = orc.satd_search(cur, refp, r, 0, nb)
+            gc, gb = x266.xSatd8x8SearchTiled(ct, rt, w, h, r)
+            assert np.array_equal(gc, wc) and np.array_equal(gb, wb)
+            dct, drt = torch.from_numpy(ct).cuda(), torch.from_numpy(rt).cuda()
+            dbest = torch.empty((nb, 3), dtype=torch.int32, device="cuda")
+            x266.xSad8x8SearchTiledDev(dct.data_ptr(), drt.data_ptr(), w, h, r, 0, nb, 0, dbest.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(dbest.cpu().numpy(), orc.sad_search(cur, refp, r, 0, nb)[1])
+
+
 # --------------------------------------------------------------------------------- SAD ("next" N4)
 def test_sad_reference_golden_dataset(x266):
     import os

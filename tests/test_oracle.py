@@ -483,3 +483,31 @@ def test_recon_loop_closes(orc):
     assert np.abs(recon.astype(np.int32) - cur).max() <= 3
     level51, recon51, _, _ = orc.intra32_encode(cur, refs[:64], refs[64:], 51)
     assert np.count_nonzero(level51) < np.count_nonzero(level) and np.abs(recon51.astype(np.int32) - cur).mean() < 25
+
+
+# ---- N2: the tiled frame format pinned against the COMPILED reference functions (oracle/_ref/libx266conv.so = xConvInputFmt /
+# ---- xConvOutput420 of src/x266.cpp:415-492 cut out of the source where it lies and compiled by oracle/ref_conv_slice.sh)
+def test_conv_restatement_equals_compiled_reference(orc):
+    from oracle import RefConv, have_ref_conv, build
+    build()
+    if not have_ref_conv():
+        pytest.skip("oracle/_ref/libx266conv.so not available")
+    rc = RefConv()
+    rng = np.random.default_rng(16)
+    for w, h, strd in ((16, 16, 16), (32, 16, 32), (176, 144, 176), (176, 144, 200), (1920, 1088, 1920)):
+        Yb = rng.integers(0, 256, strd * h, dtype=np.uint8)
+        Ub = rng.integers(0, 256, (strd >> 1) * (h // 2), dtype=np.uint8)
+        Vb = rng.integers(0, 256, (strd >> 1) * (h // 2), dtype=np.uint8)
+        tiles = np.full((w // 16) * (h // 16) * 512, 0xA5, np.uint8)
+        rc.input_fmt(Yb, Ub, Vb, strd, w, h, tiles)
+        t = tiles.reshape(-1, 512)
+        assert (t[:, 384:] == 0xA5).all()                                   # m_I is left untouched (x266.cpp:432-450 never writes it)
+        Y = Yb.reshape(h, strd)[:, :w]; U = Ub.reshape(h // 2, strd >> 1)[:, :w // 2]; V = Vb.reshape(h // 2, strd >> 1)[:, :w // 2]
+        mine = orc.conv_input_fmt(np.ascontiguousarray(Y), np.ascontiguousarray(U), np.ascontiguousarray(V)).reshape(-1, 512)
+        assert np.array_equal(mine[:, :384], t[:, :384]), (w, h, strd)
+        # and back: the compiled xConvOutput420 on the reference's tiles against the restatement's
+        oy = np.zeros(strd * h, np.uint8); ou = np.zeros((strd >> 1) * (h // 2), np.uint8); ov = np.zeros_like(ou)
+        rc.output420(tiles, oy, strd, ou, ov, strd >> 1, w, h)
+        y2, u2, v2 = orc.conv_output420(tiles, w, h)
+        assert np.array_equal(oy.reshape(h, strd)[:, :w], y2) and np.array_equal(ou.reshape(h // 2, strd >> 1)[:, :w // 2], u2)
+        assert np.array_equal(ov.reshape(h // 2, strd >> 1)[:, :w // 2], v2) and np.array_equal(y2, Y)

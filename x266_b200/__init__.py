@@ -11,7 +11,7 @@ from .binding import (  # noqa: F401
     partialButterfly32, satd8x8, g_t32,
     xDct32Batch, xDctNBatch, xSatd8x8Batch, xSatd8x8Search, xIntra32Pred,
     xDct32BatchDev, xDctNBatchDev, xSatd8x8BatchDev, xSatd8x8SearchDev, xIntra32PredDev, xPartialButterfly32Dev,
-    xFrameResiDct32, xFrameResiDct32Dev, xConvInputFmtDev, xConvOutput420Dev,
+    xFrameResiDct32, xFrameResiDct32Dev, xConvInputFmtDev, xConvOutput420Dev, xConvInputFmt, xConvOutput420, xSatd8x8SearchTiled, xSatd8x8SearchTiledDev, xSad8x8SearchTiledDev,
     xTranspose32x32Batch, xTranspose32x32BatchDev,
     xIntra32Decide, xIntra32DecideDev, xIntra32PredModes, xIntra32PredModesDev, xIntra32EncodeBlock, xIntra32EncodeBlockDev, xIntra32Recon, xIntra32ReconDev, xQuantDequantDev, xIdct32Batch, xIdct32BatchDev, xDct32BatchMultiGpu,
     sad, xSad8x8Search, xSad8x8SearchDev, xIntra32MmaTable,

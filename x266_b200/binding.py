@@ -72,6 +72,13 @@ def lib():
     _set(L, "xSatd8x8SearchDev", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp])
     _set(L, "xIntra32Pred", "argtypes", [vp, vp, vp, sz])
     _set(L, "xIntra32PredDev", "argtypes", [vp, vp, vp, sz, vp])
+    _set(L, "xConvInputFmt", "argtypes", [vp, vp, vp, vp, C.c_ssize_t, i, i])
+    _set(L, "xConvInputFmt", "restype", None)
+    _set(L, "xConvOutput420", "argtypes", [vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, i, i])
+    _set(L, "xConvOutput420", "restype", None)
+    _set(L, "xSatd8x8SearchTiled", "argtypes", [vp, vp, i, i, i, sz, sz, vp, vp])
+    _set(L, "xSatd8x8SearchTiledDev", "argtypes", [vp, vp, i, i, i, sz, sz, vp, vp, vp])
+    _set(L, "xSad8x8SearchTiledDev", "argtypes", [vp, vp, i, i, i, sz, sz, vp, vp, vp])
     _set(L, "xConvInputFmtDev", "argtypes", [vp, vp, vp, vp, C.c_ssize_t, i, i, vp])
     _set(L, "xConvOutput420Dev", "argtypes", [vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, i, i, vp])
     _set(L, "xFrameResiDct32", "argtypes", [vp, vp, i, i, vp, i, i])
@@ -351,6 +358,38 @@ def xFrameResiDct32(cur_tiles, pred_tiles, width, height, shift1st=4, shift2nd=1
     _ck(lib().xFrameResiDct32(cur_tiles.ctypes.data, pred_tiles.ctypes.data, width, height, coef.ctypes.data, shift1st, shift2nd),
         "xFrameResiDct32")
     return coef
+
+
+def xConvInputFmt(tiles, Y, U, V, strd_y, width, height):
+    """reference name and signature (src/x266.cpp:415-421): host planes -> host tiles, in place (m_I untouched)"""
+    lib().xConvInputFmt(tiles.ctypes.data, Y.ctypes.data, U.ctypes.data, V.ctypes.data, strd_y, width, height)
+    return tiles
+
+
+def xConvOutput420(tiles, Y, strd_y, U, V, strd_c, width, height):
+    """reference name and signature (src/x266.cpp:455-462): host tiles -> host planes, in place"""
+    lib().xConvOutput420(tiles.ctypes.data, Y.ctypes.data, strd_y, U.ctypes.data, V.ctypes.data, strd_c, width, height)
+
+
+def xSatd8x8SearchTiled(cur_tiles, ref_tiles, width, height, rng, blk0=0, blk1=None, want_cost=True, want_best=True):
+    cur_tiles = _np(cur_tiles, np.uint8); ref_tiles = _np(ref_tiles, np.uint8)
+    if blk1 is None:
+        blk1 = (width // 8) * (height // 8)
+    side = 2 * rng + 1
+    nb = blk1 - blk0
+    cost = np.empty((nb, side, side), np.uint32) if want_cost else None
+    best = np.empty((nb, 3), np.int32) if want_best else None
+    _ck(lib().xSatd8x8SearchTiled(cur_tiles.ctypes.data, ref_tiles.ctypes.data, width, height, rng, blk0, blk1,
+                                  cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None), "xSatd8x8SearchTiled")
+    return cost, best
+
+
+def xSatd8x8SearchTiledDev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSatd8x8SearchTiledDev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream), "xSatd8x8SearchTiledDev")
+
+
+def xSad8x8SearchTiledDev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSad8x8SearchTiledDev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream), "xSad8x8SearchTiledDev")
 
 
 def xConvInputFmtDev(d_tiles, d_y, d_u, d_v, strd_y, width, height, stream=0):

@@ -983,6 +983,144 @@ extern "C" int xConvOutput420Dev(const void* dTiles, uint8_t* dY, intptr_t strdY
     return 0;
 }
 
+// the reference's own host signatures (src/x266.cpp:415-421, 455-462): void, caller contract violations abort like its asserts
+static int conv_input_host(void* pBlock, const uint8_t* inpY, const uint8_t* inpU, const uint8_t* inpV, intptr_t strdY, int width, int height)
+{
+    if (!pBlock || !inpY || !inpU || !inpV || width <= 0 || height <= 0 || (width & 15) || (height & 15) || strdY < width)
+        return fail("xConvInputFmt", cudaSuccess);
+    PipeLease l;
+    if (!l.ok()) return -1;
+    Pipe& p = *l.p;
+    const size_t nTiles = (size_t)(width / 16) * (height / 16), lum = (size_t)width * height, chr = lum / 4;
+    const intptr_t strdC = strdY >> 1;                                // x266.cpp:426
+    if (ensure(&p.dIn[0], &p.capIn[0], lum + 2 * chr)) return -1;
+    if (ensure(&p.dOut[0], &p.capOut[0], nTiles * 512)) return -1;
+    uint8_t* dY = (uint8_t*)p.dIn[0];
+    uint8_t* dU = dY + lum;
+    uint8_t* dV = dU + chr;
+    cudaStream_t st = p.st[0];
+    CK(cudaMemcpy2DAsync(dY, width, inpY, strdY, width, height, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(dU, width / 2, inpU, strdC, width / 2, height / 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(dV, width / 2, inpV, strdC, width / 2, height / 2, cudaMemcpyHostToDevice, st));
+    CK(launch_conv_input_fmt((uint8_t*)p.dOut[0], dY, dU, dV, width, width, height, st));
+    // m_Y | m_C of every tile (384 bytes); m_I stays what the caller had there, as in the reference
+    CK(cudaMemcpy2DAsync(pBlock, 512, p.dOut[0], 512, 384, nTiles, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" void xConvInputFmt(ref_block_t* pBlock, const uint8_t* inpY, const uint8_t* inpU, const uint8_t* inpV, const intptr_t strdY,
+                              const int width, const int height)
+{
+    if (conv_input_host(pBlock, inpY, inpU, inpV, strdY, width, height)) die("xConvInputFmt");
+}
+
+static int conv_output_host(const void* pBlock, uint8_t* outY, intptr_t strdY, uint8_t* outU, uint8_t* outV, intptr_t strdC, int width, int height)
+{
+    if (!pBlock || !outY || !outU || !outV || width <= 0 || height <= 0 || (width & 15) || (height & 15) || strdY < width || strdC < width / 2)
+        return fail("xConvOutput420", cudaSuccess);
+    PipeLease l;
+    if (!l.ok()) return -1;
+    Pipe& p = *l.p;
+    const size_t nTiles = (size_t)(width / 16) * (height / 16), lum = (size_t)width * height, chr = lum / 4;
+    if (ensure(&p.dIn[0], &p.capIn[0], nTiles * 512)) return -1;
+    if (ensure(&p.dOut[0], &p.capOut[0], lum + 2 * chr)) return -1;
+    uint8_t* dY = (uint8_t*)p.dOut[0];
+    uint8_t* dU = dY + lum;
+    uint8_t* dV = dU + chr;
+    cudaStream_t st = p.st[0];
+    CK(cudaMemcpyAsync(p.dIn[0], pBlock, nTiles * 512, cudaMemcpyHostToDevice, st));
+    CK(launch_conv_output420((const uint8_t*)p.dIn[0], dY, width, dU, dV, width / 2, width, height, st));
+    CK(cudaMemcpy2DAsync(outY, strdY, dY, width, width, height, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpy2DAsync(outU, strdC, dU, width / 2, width / 2, height / 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpy2DAsync(outV, strdC, dV, width / 2, width / 2, height / 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" void xConvOutput420(const ref_block_t* pBlock, uint8_t* outY, const intptr_t strdY, uint8_t* outU, uint8_t* outV, intptr_t strdC,
+                               const int width, const int height)
+{
+    if (conv_output_host(pBlock, outY, strdY, outU, outV, strdC, width, height)) die("xConvOutput420");
+}
+
+// Full search on the encoder's own frame stores: current and reference are ref_block_t frames (m_frames[0] and m_frames[1..2],
+// src/x266.cpp:99), the reference is edge-replicated by `range` pixels here instead of by the caller.
+static int search_tiled_dev(const char* api, search_launch_t launch, const void* dCurTiles, const void* dRefTiles, int w, int h, int range,
+                            size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, cudaStream_t st)
+{
+    if (!dCurTiles || !dRefTiles || w <= 0 || h <= 0 || (w & 15) || (h & 15) || range < 0 || blk1 < blk0 || blk1 > (size_t)(w / 8) * (h / 8))
+        return fail(api, cudaSuccess);
+    if (blk1 == blk0) return 0;
+    if (dev_ready()) return -1;
+    const size_t curBytes = align256((size_t)w * h), strd = (size_t)w + 2 * range, refBytes = strd * (h + 2 * range);
+    void* planes = nullptr;
+    cudaError_t e = scratch_alloc(&planes, curBytes + refBytes, st);
+    if (e != cudaSuccess) return fail(api, e);
+    uint8_t* dCur = (uint8_t*)planes;
+    uint8_t* dRef = dCur + curBytes;
+    e = launch_tiles_to_luma((const uint8_t*)dCurTiles, w, h, 0, dCur, st);
+    if (e == cudaSuccess) e = launch_tiles_to_luma((const uint8_t*)dRefTiles, w, h, range, dRef, st);
+    if (e == cudaSuccess) e = launch(dCur, dRef, (intptr_t)strd, w, h, range, blk0, blk1, dCost, dBest, st);
+    const cudaError_t ef = scratch_free(planes, st);
+    if (e != cudaSuccess || ef != cudaSuccess) return fail(api, e != cudaSuccess ? e : ef);
+    return 0;
+}
+
+extern "C" int xSatd8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                                      uint32_t* dCost, int32_t* dBest, void* stream)
+{
+    return search_tiled_dev("xSatd8x8SearchTiledDev", launch_satd8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost, dBest,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int xSad8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                                     uint32_t* dCost, int32_t* dBest, void* stream)
+{
+    return search_tiled_dev("xSad8x8SearchTiledDev", launch_sad8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost, dBest,
+                            (cudaStream_t)stream);
+}
+
+// host form: the two frames go up once, the block range runs through the chunked pipeline like xSatd8x8Search
+extern "C" int xSatd8x8SearchTiled(const void* curTiles, const void* refTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                                   uint32_t* cost, int32_t* best)
+{
+    const char* api = "xSatd8x8SearchTiled";
+    if (!curTiles || !refTiles || width <= 0 || height <= 0 || (width & 15) || (height & 15) || range < 0 || blk1 < blk0 ||
+        blk1 > (size_t)(width / 8) * (height / 8))
+        return fail(api, cudaSuccess);
+    if (blk1 == blk0) return 0;
+    PipeLease l;
+    if (!l.ok()) return -1;
+    Pipe& p = *l.p;
+    const size_t tileBytes = (size_t)(width / 16) * (height / 16) * 512;
+    const size_t curBytes = align256((size_t)width * height), strd = (size_t)width + 2 * range, refBytes = align256(strd * (height + 2 * range));
+    if (ensure(&p.dAux, &p.capAux, 2 * tileBytes + curBytes + refBytes)) return -1;
+    uint8_t* dCurT = (uint8_t*)p.dAux;
+    uint8_t* dRefT = dCurT + tileBytes;
+    uint8_t* dCur = dRefT + tileBytes;
+    uint8_t* dRef = dCur + curBytes;
+    CK(cudaMemcpyAsync(dCurT, curTiles, tileBytes, cudaMemcpyHostToDevice, p.st[0]));
+    CK(cudaMemcpyAsync(dRefT, refTiles, tileBytes, cudaMemcpyHostToDevice, p.st[0]));
+    CK(launch_tiles_to_luma(dCurT, width, height, 0, dCur, p.st[0]));
+    CK(launch_tiles_to_luma(dRefT, width, height, range, dRef, p.st[0]));
+    CK(cudaStreamSynchronize(p.st[0]));
+    const size_t side = (size_t)(2 * range + 1), costUnit = side * side * 4;
+    size_t per = cost ? ((size_t)64 << 20) / costUnit : (size_t)1 << 20;
+    if (per < 1) per = 1;
+    const HostArr outs[2] = { { cost, costUnit }, { best, 12 } };
+    if (run_chunked_on(p, nullptr, 0, outs, 2, blk1 - blk0, per,
+                       [&](void* const*, void* const* dO, size_t u0, size_t nu, cudaStream_t st) {
+                           return launch_satd8x8_search(dCur, dRef, (intptr_t)strd, width, height, range, blk0 + u0, blk0 + u0 + nu,
+                                                        (uint32_t*)dO[0], (int32_t*)dO[1], st);
+                       })) {
+        const std::string inner(t_err);
+        snprintf(t_err, sizeof(t_err), "%s: %s", api, inner.c_str());
+        return -1;
+    }
+    return 0;
+}
+
 extern "C" int xFrameResiDct32Dev(const void* dCurTiles, const void* dPredTiles, int width, int height, int16_t* dCoef,
                                   int s1, int s2, void* stream)
 {

@@ -105,6 +105,42 @@ transpose32_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, s
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Luma of a ref_block_t frame (src/x266.cpp:56-63, tiles of 16x16) as a plane, edge-replicated by `pad` pixels on every side: what the
+// full-search kernels read.  out has stride w + 2 pad and h + 2 pad rows; pad = 0 gives the plain plane.  One thread per 4 output pixels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tiles_to_luma_kernel(const uint8_t* __restrict__ tiles, int tilesPerRow, int w, int h, int pad, uint8_t* __restrict__ out)
+{
+    const int ow = w + 2 * pad, oh = h + 2 * pad;
+    const int wordsPerRow = (ow + 3) >> 2;
+    const size_t total = (size_t)wordsPerRow * oh;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int oy = (int)(i / wordsPerRow), ox0 = (int)(i - (size_t)oy * wordsPerRow) * 4;
+        const int y = min(max(oy - pad, 0), h - 1);
+        uint8_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = min(max(ox0 + k - pad, 0), w - 1);
+            v[k] = tiles[((size_t)(y >> 4) * tilesPerRow + (x >> 4)) * 512 + (y & 15) * 16 + (x & 15)];
+        }
+        uint8_t* d = out + (size_t)oy * ow + ox0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (ox0 + k < ow) d[k] = v[k];
+    }
+}
+
+cudaError_t launch_tiles_to_luma(const uint8_t* tiles, int width, int height, int pad, uint8_t* out, cudaStream_t st)
+{
+    if (width <= 0 || height <= 0 || (width & 15) || (height & 15) || pad < 0) return cudaErrorInvalidValue;
+    const size_t total = (size_t)((width + 2 * pad + 3) / 4) * (height + 2 * pad);
+    const size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 8;
+    tiles_to_luma_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(tiles, width / 16, width, height, pad, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_transpose32(const uint8_t* src, uint8_t* dst, size_t nTiles, cudaStream_t st)
 {
     if (nTiles == 0) return cudaSuccess;

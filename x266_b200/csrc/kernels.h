@@ -32,6 +32,7 @@ cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlo
 
 cudaError_t launch_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int width, int height, int16_t* dst,
                                     int s1, int s2, cudaStream_t st);
+cudaError_t launch_tiles_to_luma(const uint8_t* tiles, int width, int height, int pad, uint8_t* out, cudaStream_t st);
 cudaError_t launch_transpose32(const uint8_t* src, uint8_t* dst, size_t nTiles, cudaStream_t st);
 cudaError_t launch_conv_input_fmt(uint8_t* tiles, const uint8_t* Y, const uint8_t* U, const uint8_t* V, intptr_t strdY,
                                   int width, int height, cudaStream_t st);
