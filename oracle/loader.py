@@ -40,7 +40,8 @@ class Oracle:
 
     def __init__(self):
         build()
-        L = self.lib = C.CDLL(os.path.join(HERE, "liboracle.so"))
+        # X266_ORACLE_LIB: another build of the same source (scripts/sanitize_cpu.sh loads the ASan + UBSan one)
+        L = self.lib = C.CDLL(os.environ.get("X266_ORACLE_LIB", os.path.join(HERE, "liboracle.so")))
         L.orc_build_g32.argtypes = [_i16p]
         L.orc_partialButterfly.argtypes = [_i16p, _i16p, C.c_int, C.c_int, C.c_int]
         L.orc_partialDense.argtypes = [_i16p, _i16p, C.c_int, C.c_int, C.c_int]

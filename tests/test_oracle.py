@@ -373,7 +373,8 @@ def test_packed_search_arithmetic_model(orc, tmp_path):
     import ctypes
     import subprocess
     so = str(tmp_path / "satd_packed_model.so")
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "c", "satd_packed_model.cpp")])
+    flags = os.environ.get("X266_TEST_CXXFLAGS", "-O2").split()             # scripts/sanitize_cpu.sh passes the sanitizer flags here
+    subprocess.check_call(["g++", *flags, "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "c", "satd_packed_model.cpp")])
     L = ctypes.CDLL(so)
     r = np.random.default_rng(0)
     H = np.array([[(-1) ** bin(a & b).count("1") for b in range(64)] for a in range(64)])
