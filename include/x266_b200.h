@@ -99,7 +99,8 @@ int xGpuSetDctVariant(int variant);
  * host-pointer DCT pipeline | 5 CUDA-core intra decision | 6 accumulate form of the v3 search | 7 first-generation SAD search | 8 CUDA-core SWAR intra interpolation |
  * 9 / 10 / 11 CTAs per SM of the intra / DCT8 / DCT4 persistent grids (0 = shipped) | 12 pageable host buffers: 0 staged through the
  * pinned ring (shipped), 1 handed to the driver, 2 cudaHostRegister per call | 13 host copy threads (0 = X266_HOST_COPY_THREADS or
- * min(8, cpus/2)) | 14 non-temporal staging copies (1 = shipped) | 15 device-side mode[] range check in the *Dev intra entry points. */
+ * min(8, cpus/2)) | 14 non-temporal staging copies (1 = shipped) | 15 device-side mode[] range check in the *Dev intra entry points |
+ * 16 fused residual + DCT32: 0 two blocks in flight per warp (shipped), 1 one. */
 int xGpuTune(int key, int value);
 
 /* 2-D forward 32x32 transform of nBlocks contiguous row-major int16 blocks:

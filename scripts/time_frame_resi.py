@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""fused residual + DCT32 from tiled frames: (prefetch depth, CTAs/SM) sweep -- xGpuTune key 16; 7680x4320 frame x 16 (4 KB per block)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import x266_b200 as xb
+dev = torch.device("cuda:0")
+w, h = 7680, 4320 * 16 // 16 * 16
+h = 4320 * 16
+nt = (w // 16) * (h // 16)
+g = torch.Generator(device=dev); g.manual_seed(1)
+cur = torch.randint(0, 256, (nt * 512,), device=dev, generator=g, dtype=torch.uint8)
+prd = torch.randint(0, 256, (nt * 512,), device=dev, generator=g, dtype=torch.uint8)
+nb = (w // 32) * (h // 32)
+coef = torch.empty((nb, 1024), device=dev, dtype=torch.int16)
+st = torch.cuda.current_stream().cuda_stream
+names = {0: "depth 1, 2 CTAs/SM (round 1)", 1: "depth 2, 2", 2: "depth 1, 3", 3: "depth 2, 3", 4: "depth 3, 2", 5: "depth 1, 4"}
+ref = None
+for cfg in (0, 1, 2, 3, 4, 5, 0):
+    xb.tune(16, cfg)
+    for _ in range(3):
+        xb.xFrameResiDct32Dev(cur.data_ptr(), prd.data_ptr(), w, h, coef.data_ptr(), 4, 11, st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        xb.xFrameResiDct32Dev(cur.data_ptr(), prd.data_ptr(), w, h, coef.data_ptr(), 4, 11, st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    same = True if ref is None else bool(torch.equal(coef, ref))
+    if ref is None:
+        ref = coef.clone()
+    print(f"cfg {cfg} ({names[cfg]}): {ms:.4f} ms  {nb / ms / 1e6:.3f} G blocks/s  {nb * 4096 / ms / 1e6 / 6459.3:.3f} of HBM  same={same}", flush=True)
+xb.tune(16, 0)

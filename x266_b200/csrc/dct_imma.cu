@@ -412,7 +412,9 @@ cudaError_t launch_dct8_imma(const int16_t* src, int16_t* dst, size_t nBlocks, i
 // ------------------------------------------------------------------------------------------------
 constexpr int FR_WARPS = 8;
 
-__global__ void __launch_bounds__(FR_WARPS * 32, 2)
+// DEPTH = blocks whose pixels are in flight (registers) ahead of the one being transformed, MINB = CTAs per SM
+template <int DEPTH, int MINB>
+__global__ void __launch_bounds__(FR_WARPS * 32, MINB)
 frame_resi_dct32_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ pred, int tilesPerRow, int blocksPerRow,
                         size_t nBlocks, int16_t* __restrict__ dst, int shift1, int shift2)
 {
@@ -455,14 +457,20 @@ frame_resi_dct32_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
         }
     };
 
-    uint2 nc[4] = {}, np[4] = {};
-    if (first < nBlocks) load_block(first, nc, np);
+    uint2 nc[DEPTH][4] = {}, np[DEPTH][4] = {};
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++)
+        if (first + d * stride < nBlocks) load_block(first + d * stride, nc[d], np[d]);
 
     for (size_t b = first; b < nBlocks; b += stride) {
         uint2 bc[4], bp[4];
 #pragma unroll
-        for (int t = 0; t < 4; t++) { bc[t] = nc[t]; bp[t] = np[t]; }
-        if (b + stride < nBlocks) load_block(b + stride, nc, np);
+        for (int t = 0; t < 4; t++) { bc[t] = nc[0][t]; bp[t] = np[0][t]; }
+#pragma unroll
+        for (int d = 0; d + 1 < DEPTH; d++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) { nc[d][t] = nc[d + 1][t]; np[d][t] = np[d + 1][t]; }
+        if (b + DEPTH * stride < nBlocks) load_block(b + DEPTH * stride, nc[DEPTH - 1], np[DEPTH - 1]);
 
         uint32_t B2L[4][2], B2H[4][2];
 #pragma unroll
@@ -511,14 +519,23 @@ frame_resi_dct32_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
     }
 }
 
+static std::atomic<int> g_frameResiCfg{0};   // tuning/diagnostic: 0 = two blocks in flight per warp (shipped), 1 = one (round 1)
+void set_frame_resi_config(int v) { g_frameResiCfg = v; }
+
 cudaError_t launch_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int width, int height, int16_t* dst,
                                     int s1, int s2, cudaStream_t st)
 {
     if (width <= 0 || height <= 0 || (width & 31) || (height & 31)) return cudaErrorInvalidValue;
     const size_t nBlocks = (size_t)(width / 32) * (height / 32);
     const size_t want = (nBlocks + FR_WARPS - 1) / FR_WARPS;
-    const size_t cap = (size_t)sm_count() * 2;
-    frame_resi_dct32_kernel<<<(int)(want < cap ? want : cap), FR_WARPS * 32, 0, st>>>(cur, pred, width / 16, width / 32, nBlocks, dst, s1, s2);
+    auto go = [&](auto kern, int ctas) {
+        const size_t cap = (size_t)sm_count() * ctas;
+        kern<<<(int)(want < cap ? want : cap), FR_WARPS * 32, 0, st>>>(cur, pred, width / 16, width / 32, nBlocks, dst, s1, s2);
+    };
+    // measured on 16 stacked 8K frames (profiles/r02_frame_resi_sweep.log): depth 2 at 2 CTAs/SM 0.959 of the HBM roofline, depth 1 0.941-0.946,
+    // depth 3 0.936 (126 -> 128 registers, nothing left for the MMA section), 3 or 4 CTAs/SM 0.69-0.85 (register spills)
+    if (g_frameResiCfg.load() == 1) go(frame_resi_dct32_kernel<1, 2>, 2);
+    else go(frame_resi_dct32_kernel<2, 2>, 2);
     count_launch();
     return cudaGetLastError();
 }

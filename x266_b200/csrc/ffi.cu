@@ -551,6 +551,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 13 && value >= 0) { set_host_copy_threads(value); return 0; }
     if (key == 14) { set_host_copy_nt(value); return 0; }
     if (key == 15) { g_checkModes.store(value ? 1 : 0); return 0; }
+    if (key == 16) { set_frame_resi_config(value); return 0; }
     return fail("xGpuTune: unknown key", cudaSuccess);
 }
 

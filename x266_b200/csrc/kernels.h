@@ -30,6 +30,7 @@ void set_search_v1(int on);     // tuning/diagnostic: 0 = v3 (default), 1 = v1 (
 cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int line, cudaStream_t st);
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st);
 
+void set_frame_resi_config(int v);   // tuning/diagnostic: (prefetch depth, CTAs/SM) of the fused residual + DCT32 kernel
 cudaError_t launch_frame_resi_dct32(const uint8_t* cur, const uint8_t* pred, int width, int height, int16_t* dst,
                                     int s1, int s2, cudaStream_t st);
 cudaError_t launch_tiles_to_luma(const uint8_t* tiles, int width, int height, int pad, uint8_t* out, cudaStream_t st);
