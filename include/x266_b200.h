@@ -94,12 +94,13 @@ enum {
 };
 int xGpuSetDctVariant(int variant);
 /* Diagnostic/tuning hook (not part of the reference-facing surface; 0 / -1 = shipped default everywhere):
- * key 0 IMMA DCT32 instantiation (warps, stages, CTAs/SM, staging; scripts/tune_dct.py) | 1 SATD search kernel (0 v3 packed
- * transform domain, 1 one CTA per block, 2/3 v2 strips) | 2 SATD batch variant | 3 CUDA-core DCT 8/16 | 4 blocks per chunk of the
- * host-pointer DCT pipeline | 5 CUDA-core intra decision | 6 accumulate form of the v3 search | 7 first-generation SAD search | 8 CUDA-core SWAR intra interpolation |
+ * key 0 IMMA DCT32 instantiation (0 / 3 TMA rings, 6 direct loads = shipped, 7, 12; scripts/tune_dct.py) | 1 SATD search kernel (0 v3 packed
+ * transform domain, 1 one CTA per block for any range) | 2 SATD batch (0 tensor cores + 3-stage ring, 1 CUDA cores, 5 4-stage ring) | 3 CUDA-core
+ * DCT 4/8/16 | 4 blocks per chunk of the host-pointer DCT pipeline | 5 (unused) | 6 accumulate form of the v3 search | 7 first-generation SAD search |
+ * 8 CUDA-core SWAR intra interpolation |
  * 9 / 10 / 11 CTAs per SM of the intra / DCT8 / DCT4 persistent grids (0 = shipped) | 12 pageable host buffers: 0 staged through the
  * pinned ring (shipped), 1 handed to the driver, 2 cudaHostRegister per call | 13 host copy threads (0 = X266_HOST_COPY_THREADS or
- * min(8, cpus/2)) | 14 non-temporal staging copies (1 = shipped) | 15 device-side mode[] range check in the *Dev intra entry points |
+ * min(8, cpus/2)) | 14 non-temporal staging copies, bit 0 into the pinned slots, bit 1 into caller memory (3 = shipped) | 15 device-side mode[] range check in the *Dev intra entry points |
  * 16 fused residual + DCT32: 0 two blocks in flight per warp (shipped), 1 one. */
 int xGpuTune(int key, int value);
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""fused residual + DCT32 from tiled frames: (prefetch depth, CTAs/SM) sweep -- xGpuTune key 16; 7680x4320 frame x 16 (4 KB per block)."""
+"""fused residual + DCT32 from tiled frames: blocks in flight per warp (xGpuTune key 16; the full depth / occupancy sweep is
+profiles/r02_frame_resi_sweep.log); 16 stacked 8K frames, 4 KB per block."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,9 +15,9 @@ prd = torch.randint(0, 256, (nt * 512,), device=dev, generator=g, dtype=torch.ui
 nb = (w // 32) * (h // 32)
 coef = torch.empty((nb, 1024), device=dev, dtype=torch.int16)
 st = torch.cuda.current_stream().cuda_stream
-names = {0: "depth 1, 2 CTAs/SM (round 1)", 1: "depth 2, 2", 2: "depth 1, 3", 3: "depth 2, 3", 4: "depth 3, 2", 5: "depth 1, 4"}
+names = {0: "two blocks in flight per warp, 2 CTAs/SM (shipped)", 1: "one block in flight (round 1)"}
 ref = None
-for cfg in (0, 1, 2, 3, 4, 5, 0):
+for cfg in (0, 1, 0, 1):
     xb.tune(16, cfg)
     for _ in range(3):
         xb.xFrameResiDct32Dev(cur.data_ptr(), prd.data_ptr(), w, h, coef.data_ptr(), 4, 11, st)

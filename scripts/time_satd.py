@@ -9,8 +9,8 @@ n = 1 << 24
 st = torch.cuda.current_stream().cuda_stream
 for rng, name in ((256, "9-bit"), (32768, "full int16")):
     d = torch.randint(-rng + 1 if rng == 256 else -rng, rng, (n, 64), device=dev, dtype=torch.int16)
-    o = [torch.empty(n, device=dev, dtype=torch.int32) for _ in range(6)]
-    for v in (0, 1, 2, 3, 4, 5):
+    o = {v: torch.empty(n, device=dev, dtype=torch.int32) for v in (0, 1, 5)}
+    for v in (0, 1, 5):
         xb.tune(2, v)
         for _ in range(3):
             xb.xSatd8x8BatchDev(d.data_ptr(), o[v].data_ptr(), n, st)
@@ -20,6 +20,6 @@ for rng, name in ((256, "9-bit"), (32768, "full int16")):
             xb.xSatd8x8BatchDev(d.data_ptr(), o[v].data_ptr(), n, st)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"satd batch {('v2 ring3','cuda-core','imma v1','v2 3cta','v2 direct','v2 ring4')[v]:9s} {name:10s}: {ms:.3f} ms  {n/ms/1e6:.2f} G cand/s  {n*132/ms/1e6:.0f} GB/s  {n*132/ms/1e6/6545.6*100:.1f}% of measured HBM", flush=True)
-    print("  all equal:", all(torch.equal(o[0], o[k]) for k in (1, 2, 3, 4, 5)))
+        print(f"satd batch { {0: 'ring, 3 stages', 1: 'cuda-core', 5: 'ring, 4 stages'}[v]:14s} {name:10s}: {ms:.3f} ms  {n/ms/1e6:.2f} G cand/s  {n*132/ms/1e6:.0f} GB/s  {n*132/ms/1e6/6459.3*100:.1f}% of measured HBM", flush=True)
+    print("  all equal:", all(torch.equal(o[0], o[k]) for k in (1, 5)))
 xb.tune(2, 0)

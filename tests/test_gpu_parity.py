@@ -149,7 +149,7 @@ def test_bdpi_stream_against_live_reference(x266, ref):
 # ------------------------------------------------------------------------------------ DCT N<32
 @pytest.mark.parametrize("log2n", [2, 3, 4])
 @pytest.mark.parametrize("nblk", [1, 2, 3, 4, 5, 64, 1000, 4097, 75777])
-@pytest.mark.parametrize("cuda_core", [0, 1, 2])
+@pytest.mark.parametrize("cuda_core", [0, 1])
 def test_dctN(x266, orc, log2n, nblk, cuda_core):
     """N<32: tensor-core kernels where they exist (tune 3 = 0) and the CUDA-core dctN kernels (tune 3 = 1)"""
     n = 1 << log2n
@@ -179,12 +179,12 @@ def test_config4_mixed_partition(x266, orc):
 
 
 # ---------------------------------------------------------------------------------------- SATD
-SATD_VARIANTS = ["imma-v2-ring3", "cuda-core", "imma-v1", "imma-v2-3cta", "imma-v2-direct", "imma-v2-ring4"]
+SATD_VARIANTS = {"imma-ring3": 0, "cuda-core": 1, "imma-ring4": 5}      # xGpuTune(2, id)
 
 
 @pytest.fixture(params=SATD_VARIANTS)
 def satd_variant(request, x266):
-    x266.tune(2, SATD_VARIANTS.index(request.param))
+    x266.tune(2, SATD_VARIANTS[request.param])
     yield request.param
     x266.tune(2, 0)
 
@@ -224,10 +224,10 @@ def make_frames(w, h, rng_px, seed=266):
 
 
 @pytest.mark.parametrize("rng_px", [0, 3, 8, 16, 32])
-@pytest.mark.parametrize("v1", [0, 1, 2])
+@pytest.mark.parametrize("v1", [0, 1])
 def test_satd_search_small(x266, orc, rng_px, v1):
-    """all search kernels (0: v3 packed transform domain, two positions per thread; 1: v1 CTA per block;
-    2: v2 transform-domain strips; v2/v3 exist for R in {8,16,32}, other ranges take v1)"""
+    """both search kernels (0: v3 packed transform domain, two positions per thread, R in {8,16,32}; 1: one CTA per block, any range --
+    other ranges take it anyway)"""
     x266.tune(1, v1)
     cur, refp = make_frames(64, 48, rng_px)
     cost, best = x266.xSatd8x8Search(cur, refp, rng_px)
@@ -562,9 +562,9 @@ def test_sad_search_wide_frame_and_ties(x266, orc, rng_px):
 
 
 # ------------------------------------------------------------------ fused intra mode decision ("next" N1)
-@pytest.mark.parametrize("v1", [0, 1])
+@pytest.mark.parametrize("v1", [0])
 def test_intra32_decide(x266, orc, v1):
-    """v1 = 0: tensor-core kernel (horizontal modes on the transposed problem); v1 = 1: CUDA-core kernel"""
+    """the tensor-core decision kernel (horizontal modes on the transposed problem)"""
     x266.tune(5, v1)
     r = np.random.default_rng(12)
     n = 40
@@ -641,9 +641,9 @@ def test_full_size_config5_two_implementations_agree(x266, orc):
     assert np.array_equal(ys, orc.dct(xs, 5, 6, 11, threads=8))
 
 
-@pytest.mark.parametrize("cfg", list(range(16)))
+@pytest.mark.parametrize("cfg", [0, 3, 6, 7, 12])
 def test_every_imma_instantiation_is_bit_exact(x266, orc, cfg):
-    """all 16 (warps, stages, CTAs/SM, staging) instantiations of the tensor-core kernel, ragged batch"""
+    """every kept (warps, stages, CTAs/SM, staging) instantiation of the tensor-core kernel (TMA rings and direct loads), ragged batch"""
     x = orc.residual(5003 * 1024, 40 + cfg, 2)
     want = orc.dct(x.reshape(-1, 32, 32), 5, 4, 11, threads=8).ravel()
     x266.set_dct_variant(x266.DCT_IMMA)

@@ -205,47 +205,6 @@ dctN_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t n
 }
 
 // ------------------------------------------------------------------------------------------------
-// 4x4 blocks, one block (32 bytes) per thread, both passes and the transpose in registers, no shared memory.
-// Adjacent lanes own adjacent blocks, so the two 128-bit loads (and stores) of a warp cover one contiguous
-// 1 KiB span; the half-used sectors of the first access are completed by the second out of L1 / merged in L2.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-dct4_reg_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
-{
-    const int add1 = 1 << (shift1 - 1), add2 = 1 << (shift2 - 1);
-    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nBlocks; b += (size_t)gridDim.x * blockDim.x) {
-        const uint4 w0 = ld_global_nc(src + b * 16), w1 = ld_global_nc(src + b * 16 + 8);
-        const uint32_t w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
-        int c[4][4];                                   // c[k][j] = pass-1 output (transposed store)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int x[4], y[4];
-            x[0] = (int)(short)(w[2 * j] & 0xFFFF); x[1] = (int)w[2 * j] >> 16;
-            x[2] = (int)(short)(w[2 * j + 1] & 0xFFFF); x[3] = (int)w[2 * j + 1] >> 16;
-            Dct1D<4, 1, 4>::run(x, y);
-#pragma unroll
-            for (int k = 0; k < 4; k++) c[k][j] = (int)(short)((y[k] + add1) >> shift1);
-        }
-        uint32_t o[8];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int y[4];
-            Dct1D<4, 1, 4>::run(c[k], y);
-            // dct[k2][k]: column k of the output; gather into row-major words below
-#pragma unroll
-            for (int k2 = 0; k2 < 4; k2++) c[k][k2] = (y[k2] + add2) >> shift2;      // reuse c as out[k2][k] transposed
-        }
-#pragma unroll
-        for (int k2 = 0; k2 < 4; k2++) {
-            o[2 * k2] = prmt((uint32_t)c[0][k2], (uint32_t)c[1][k2], 0x5410);
-            o[2 * k2 + 1] = prmt((uint32_t)c[2][k2], (uint32_t)c[3][k2], 0x5410);
-        }
-        *reinterpret_cast<uint4*>(dst + b * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(dst + b * 16 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // 4x4 blocks, fully coalesced variant: a warp moves 2 KiB (64 blocks) per iteration with four 512-byte
 // load instructions; lane pairs then swap 16-byte halves (8 SHFL) so that every lane owns two whole blocks,
 // transforms them in registers, swaps the halves back (8 SHFL) and stores with four 512-byte instructions.
@@ -358,7 +317,7 @@ cudaError_t launch_partial32(const int16_t* src, int16_t* dst, int shift, int li
     return cudaGetLastError();
 }
 
-static std::atomic<int> g_smallCuda{0};     // 0: shipped (IMMA for N=8,16; lane-exchange kernel for N=4); 1: smem-staged dctN kernels; 2: N=4 one block per thread
+static std::atomic<int> g_smallCuda{0};     // 0: shipped (IMMA for N=8,16; lane-exchange kernel for N=4); 1: smem-staged CUDA-core dctN kernels
 void set_small_dct_cuda_cores(int on) { g_smallCuda = on; }
 
 cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlocks, int s1, int s2, cudaStream_t st)
@@ -366,13 +325,8 @@ cudaError_t launch_dctN(int log2n, const int16_t* src, int16_t* dst, size_t nBlo
     if (nBlocks == 0) return cudaSuccess;
     if (log2n == 4 && g_smallCuda != 1) return launch_dct16_imma(src, dst, nBlocks, s1, s2, st);
     if (log2n == 3 && g_smallCuda != 1) return launch_dct8_imma(src, dst, nBlocks, s1, s2, st);
-    if (log2n == 2 && g_smallCuda == 0) {
+    if (log2n == 2 && g_smallCuda != 1) {
         dct4_xchg_kernel<<<grid_for((nBlocks + 63) / 64, DCT4X_WARPS, g_dct4Ctas > 0 ? g_dct4Ctas.load() : 12), DCT4X_WARPS * 32, 0, st>>>(src, dst, nBlocks, s1, s2);
-        count_launch();
-        return cudaGetLastError();
-    }
-    if (log2n == 2 && g_smallCuda == 2) {
-        dct4_reg_kernel<<<grid_for(nBlocks, 256, 8), 256, 0, st>>>(src, dst, nBlocks, s1, s2);
         count_launch();
         return cudaGetLastError();
     }

@@ -557,118 +557,9 @@ intra32_kernel(const uint8_t* __restrict__ refs, const uint8_t* __restrict__ mod
 // generated in registers, subtracted from the current block and costed with the reference SATD
 // (src_tb/satd.c:31-118) on its 16 8x8 sub-blocks:  cost[mode] = sum_sb ((sum|H d H^T| + 2) >> 2).
 // Neither the prediction nor the residual ever reaches HBM (1 KiB + 129 B in, 35 x 4 B out per block).
-// One CTA per block; a half-warp owns one mode at a time, lane <-> 8x8 sub-block.
+// (A first CUDA-core version -- one half-warp per mode, lane <-> sub-block, 10.1 M blocks/s -- was replaced by the
+// tensor-core form below, 45-50 M blocks/s.)
 // ------------------------------------------------------------------------------------------------
-
-template <int STRIDE>
-__device__ __forceinline__ void had8i(int* v)
-{
-#pragma unroll
-    for (int dist = 4; dist >= 1; dist >>= 1)
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (!(i & dist)) {
-                const int a = v[i * STRIDE], b = v[(i + dist) * STRIDE];
-                v[i * STRIDE] = a + b;
-                v[(i + dist) * STRIDE] = a - b;
-            }
-}
-
-__global__ void __launch_bounds__(IDEC_WARPS * 32)
-intra32_decide_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refs, uint32_t* __restrict__ cost,
-                      int32_t* __restrict__ bestMode, size_t n)
-{
-    __shared__ __align__(16) uint8_t scur[1024];
-    __shared__ uint8_t sraw[144];
-    __shared__ __align__(16) uint8_t strip[IDEC_WARPS * 2][INTRA_STRIP];
-    __shared__ uint32_t scost[35];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int half = lane >> 4, sb = lane & 15;
-    const int sx = (sb & 3) * 8, sy = (sb >> 2) * 8;
-    uint8_t* sref = strip[warp * 2 + half] + 32;
-
-    for (size_t p = blockIdx.x; p < n; p += gridDim.x) {
-        reinterpret_cast<uint32_t*>(scur)[tid] = reinterpret_cast<const uint32_t*>(cur + p * 1024)[tid];
-        if (tid < 129) sraw[tid] = refs[p * 129 + tid];
-        __syncthreads();
-        const uint8_t* left = sraw;
-        const uint8_t* top = sraw + 64;
-
-        for (int m0 = warp * 2; m0 < 35; m0 += IDEC_WARPS * 2) {
-            const int mode = m0 + half;
-            const bool active = mode < 35;
-            const int md = active ? mode : 1;
-            const bool isVer = md >= 18;
-            const int ang = c_intraAngle[md];
-            // ---- per-mode reference strip, built by the 16 lanes of this half-warp
-            if (md >= 2) {
-                for (int i = sb; i <= 65; i += 16) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
-                if (ang < 0) {
-                    int inv = 0;
-#pragma unroll
-                    for (int a = 0; a < 8; a++) if (c_intraAngle[11 + a] == ang) inv = c_intraInv[a];
-                    for (int k = sb + 1; k <= 32; k += 16)
-                        if (-k >= ang) {
-                            const int s = (k * inv + 128) >> 8;
-                            sref[-k] = isVer ? left[s - 1] : top[s];
-                        }
-                }
-            }
-            int dc = 0;
-            if (md == 1) {
-                for (int i = 0; i < 32; i++) dc += left[i] + top[1 + i];
-                dc = (dc + 32) >> 6;
-            }
-            __syncwarp();
-            // ---- residual of this lane's 8x8 sub-block
-            int d[64];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int row = sy + r;
-                const uint2 cw = *reinterpret_cast<const uint2*>(scur + row * 32 + sx);
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const int col = sx + c;
-                    int v;
-                    if (md >= 2) {
-                        const int xr = isVer ? col : row, yd = isVer ? row : col;
-                        const int t = (yd + 1) * ang, idx = t >> 5, f = t & 31;
-                        v = ((32 - f) * sref[xr + idx + 1] + f * sref[xr + idx + 2] + 16) >> 5;
-                    } else if (md == 1) {
-                        v = dc;
-                    } else {
-                        v = ((31 - col) * left[row] + (col + 1) * top[33] + (31 - row) * top[1 + col] + (row + 1) * left[32] + 32) >> 6;
-                    }
-                    const int px = (int)(((c < 4 ? cw.x : cw.y) >> (8 * (c & 3))) & 0xFF);
-                    d[r * 8 + c] = px - v;
-                }
-                had8i<1>(&d[r * 8]);
-            }
-            unsigned sad = 0;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                had8i<8>(&d[c]);
-#pragma unroll
-                for (int r = 0; r < 8; r++) sad = __sad(d[r * 8 + c], 0, sad);   // 9-bit residuals: no int16 wrap reachable
-            }
-            unsigned c4 = (sad + 2) >> 2;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) c4 += __shfl_xor_sync(0xffffffffu, c4, o);      // sum over the 16 sub-blocks
-            if (active && sb == 0) scost[mode] = c4;
-            __syncwarp();
-        }
-        __syncthreads();
-        if (tid < 35) cost[p * 35 + tid] = scost[tid];
-        if (tid == 0) {
-            unsigned bc = scost[0];
-            int bm = 0;
-            for (int m = 1; m < 35; m++) if (scost[m] < bc) { bc = scost[m]; bm = m; }
-            bestMode[p] = bm;
-        }
-        __syncthreads();
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Mode decision v2 (shipped): the 16 sub-blocks of one (block, mode) are exactly one m16 tile of the
 // tensor-core SATD (satd.cu): A = the 8-bit prediction pixels (a single u8 plane, no byte split), B = the +-1
@@ -700,16 +591,13 @@ intra32_decide_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     }
 }
 
-static std::atomic<int> g_decideV1{0};
-void set_decide_v1(int on) { g_decideV1 = on; }
+void set_decide_v1(int) {}             // (xGpuTune key 5 selected the removed CUDA-core decision kernel; kept as a no-op for old scripts)
 
 cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    const void* kern = g_decideV1 ? (const void*)intra32_decide_kernel : (const void*)intra32_decide_v2_kernel;
-    const size_t cap = (size_t)sm_count() * resident_ctas_per_sm(kern, IDEC_WARPS * 32, 0);
-    if (g_decideV1) intra32_decide_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
-    else intra32_decide_v2_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
+    const size_t cap = (size_t)sm_count() * resident_ctas_per_sm((const void*)intra32_decide_v2_kernel, IDEC_WARPS * 32, 0);
+    intra32_decide_v2_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
     count_launch();
     return cudaGetLastError();
 }

@@ -115,111 +115,18 @@ satd8x8_batch_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out
 }
 
 // ------------------------------------------------------------------------------------------------
-// Batch on the int8 tensor cores (shipped default).  The 2-D Hadamard of an 8x8 block is the 64x64
+// Batch on the int8 tensor cores.  The 2-D Hadamard of an 8x8 block is the 64x64
 // Sylvester matrix H64[n][p] = (-1)^popcount(n&p) applied to the 64 samples, so for 16 candidates at a
 // time   D[cand][n] = sum_p diff[cand][p] * H64[n][p]   is an m16 x n64 x k64 integer product.  As in the
 // DCT kernel the int16 samples are split into byte planes (lo u8, hi s8; +-1 fits s8):
 //     D = D_lo + 256 * D_hi     (exact in s32; only D mod 2^16 matters = the reference's int16 wrap)
-// 32 x mma.sync.m16n8k32 per 16 candidates (2 k-steps x 8 n-tiles x 2 planes).  The candidate rows are
-// the A operand, read straight from global memory with 128-bit loads (row-major A == the 128-byte
-// candidate), register double-buffered; the K order is permuted so that each lane's A registers come
-// from one 16-byte chunk (the +-1 matrix columns are permuted to match, held in 32 registers).
-// Epilogue per lane: 32 coefficients -> IMAD (lo + 256 hi), sign-extend 16, VABSDIFF-accumulate; a quad
-// shuffle reduction gives the two costs of rows g and g+8.   ~10 warp instructions per candidate instead
-// of ~24 on CUDA cores (759 thread instructions per candidate measured, ALU-pipe bound at 77 %).
+// That full product is 32 x mma.sync.m16n8k32 per 16 candidates (2 k-steps x 8 n-tiles x 2 planes; round 1 measured it at 0.81 of the
+// roofline); the shipped kernel below halves it with H64 = H2 (x) H32.  The candidate rows are the A operand (row-major A == the
+// 128-byte candidate); the K order is permuted so that each lane's A registers come from one 16-byte chunk (the +-1 matrix columns are
+// permuted to match).  Epilogue per lane: coefficients -> IMAD (lo + 256 hi), pack to int16 (= the reference's wrap), packed |x|,
+// IDP.2A accumulate; a quad shuffle reduction gives the two costs of rows g and g+8.
 // ------------------------------------------------------------------------------------------------
 constexpr int SATDI_WARPS = 8;
-
-template <int MINB, int PF>      // PF = units in flight ahead of the one being transformed
-__global__ void __launch_bounds__(SATDI_WARPS * 32, MINB)
-satd8x8_imma_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, q = lane & 3;
-
-    // B fragments of the permuted +-1 matrix: k-step s, n-tile t; K position 4q+i <-> sample 32s+8q+i,
-    // K position 16+4q+i <-> sample 32s+8q+4+i; column n = 8t+g.
-    uint32_t B[2][8][2];
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-        for (int t = 0; t < 8; t++)
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int pix = 32 * s + 8 * q + 4 * r + i;
-                    const int nn = 8 * t + g;
-                    v |= ((__popc(nn & pix) & 1) ? 0xFFu : 0x01u) << (8 * i);
-                }
-                B[s][t][r] = v;
-            }
-
-    const size_t nUnits = (n + 15) / 16;
-    const size_t first = (size_t)blockIdx.x * SATDI_WARPS + warp;
-    const size_t stride = (size_t)gridDim.x * SATDI_WARPS;
-    const int cZero[4] = { 0, 0, 0, 0 };
-
-    // lane loads: row g and row g+8 of the unit, 16-byte chunk q of each 64-byte half s
-    auto load_unit = [&](size_t u, uint4 (&w)[2][2]) {
-        size_t c0 = u * 16 + g, c1 = c0 + 8;
-        c0 = c0 < n ? c0 : n - 1;           // clamp the ragged tail (results of clamped rows are not stored)
-        c1 = c1 < n ? c1 : n - 1;
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            w[s][0] = ld_global_nc(diff + c0 * 64 + 32 * s + 8 * q);
-            w[s][1] = ld_global_nc(diff + c1 * 64 + 32 * s + 8 * q);
-        }
-    };
-
-    uint4 nxt[PF][2][2] = {};
-#pragma unroll
-    for (int k = 0; k < PF; k++)
-        if (first + (size_t)k * stride < nUnits) load_unit(first + (size_t)k * stride, nxt[k]);
-
-    for (size_t u = first; u < nUnits; u += stride) {
-        // A fragments per plane and k-step: a0 (row g, K 4q+i), a1 (row g+8, same K), a2 (row g, K 16+4q+i), a3 (row g+8)
-        uint32_t AL[2][4], AH[2][4];
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const uint4 r0 = nxt[0][s][0], r1 = nxt[0][s][1];
-            AL[s][0] = prmt(r0.x, r0.y, 0x6420); AH[s][0] = prmt(r0.x, r0.y, 0x7531);
-            AL[s][2] = prmt(r0.z, r0.w, 0x6420); AH[s][2] = prmt(r0.z, r0.w, 0x7531);
-            AL[s][1] = prmt(r1.x, r1.y, 0x6420); AH[s][1] = prmt(r1.x, r1.y, 0x7531);
-            AL[s][3] = prmt(r1.z, r1.w, 0x6420); AH[s][3] = prmt(r1.z, r1.w, 0x7531);
-        }
-#pragma unroll
-        for (int k = 0; k + 1 < PF; k++)
-#pragma unroll
-            for (int s = 0; s < 2; s++) { nxt[k][s][0] = nxt[k + 1][s][0]; nxt[k][s][1] = nxt[k + 1][s][1]; }
-        if (u + (size_t)PF * stride < nUnits) load_unit(u + (size_t)PF * stride, nxt[PF - 1]);
-
-        unsigned s0a = 0, s0b = 0, s1a = 0, s1b = 0;      // row g (c0,c1) and row g+8 (c2,c3), two chains each
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-            int dl[4], dh[4];
-            mma_u8s8(dl, AL[0], B[0][t][0], B[0][t][1], cZero);
-            mma_u8s8(dl, AL[1], B[1][t][0], B[1][t][1], dl);
-            mma_s8s8(dh, AH[0], B[0][t][0], B[0][t][1], cZero);
-            mma_s8s8(dh, AH[1], B[1][t][0], B[1][t][1], dh);
-            const int v0 = (int)(short)(dl[0] + dh[0] * 256);
-            const int v1 = (int)(short)(dl[1] + dh[1] * 256);
-            const int v2 = (int)(short)(dl[2] + dh[2] * 256);
-            const int v3 = (int)(short)(dl[3] + dh[3] * 256);
-            s0a = __sad(v0, 0, s0a); s0b = __sad(v1, 0, s0b);
-            s1a = __sad(v2, 0, s1a); s1b = __sad(v3, 0, s1b);
-        }
-        unsigned sad0 = s0a + s0b, sad1 = s1a + s1b;
-        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 1); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 1);
-        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 2); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 2);
-        if (q == 0) {
-            const size_t c0 = u * 16 + g;
-            if (c0 < n) out[c0] = (int)((sad0 + 2) >> 2);
-            if (c0 + 8 < n) out[c0 + 8] = (int)((sad1 + 2) >> 2);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Full search.  One CTA per 8x8 current block; the (8+2R)^2 reference window lives in shared memory.
@@ -340,193 +247,8 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Full search v2 (R in {8,16,32}): transform-domain, one CTA per strip of NB=16 horizontally adjacent
-// blocks.  For every search row my the CTA computes, once, the full 2-D Hadamard T[p] of the reference
-// window at each of the P = 8*(NB-1)+2R+1 horizontal positions p (thread p keeps its 64 coefficients in
-// registers: vertical half V from the smem window, horizontal half from V).  Position p serves every
-// block i of the strip with 0 <= p-8i <= 2R, i.e. at most R/4+1 blocks ("slots"); the cost of candidate
-// (i, mx=p-8i, my) is sum_k |T[p][k] - Tcur_i[k]| (exact: 8-bit pixels cannot wrap int16), 64 VABSDIFF
-// fed by 16 broadcast-ish 128-bit smem loads of Tcur_i.  ~130 instructions per candidate instead of
-// ~300 (v1) / 577 (direct), and the 2R+1 = 65 candidates-per-row raggedness costs 10 % of the lanes
-// instead of 33 %.
-// ------------------------------------------------------------------------------------------------
-constexpr int S2_NB = 16;
-constexpr int S2_TC_STRIDE = 68;     // 64 coefficients + 4 words of padding: distinct blocks hit distinct banks
-constexpr int S2_VW = 40;            // per-warp V tile: 32 positions + 7 halo columns (+1 pad)
-
-template <int R, int MINB>
-__global__ void __launch_bounds__(((8 * S2_NB + 2 * R + 31) / 32) * 32, MINB)
-satd8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w,
-                         size_t blk0, size_t blk1, uint32_t* __restrict__ cost, int32_t* __restrict__ best)
-{
-    constexpr int COLS = 8 * S2_NB + 2 * R;
-    constexpr int NT = ((COLS + 31) / 32) * 32;
-    constexpr int NW = NT / 32;
-    constexpr int SIDE = 2 * R + 1;
-    constexpr int WS = 2 * R + 8;
-    constexpr int SLOTS = R / 4 + 1;
-    constexpr int WROW = NT + 8;                 // every lane of the last warp may touch column 32*(NW-1)+38
-    __shared__ uint8_t win[WS][WROW];
-    __shared__ int V[NW][8][S2_VW];
-    __shared__ __align__(16) int tcur[S2_NB][S2_TC_STRIDE];
-    __shared__ unsigned long long sBest[S2_NB];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bw = w >> 3;
-    const int i0 = blockIdx.x * S2_NB;
-    const int nb = (bw - i0) < S2_NB ? (bw - i0) : S2_NB;
-    const int by = blockIdx.y * 8, bx0 = i0 * 8;
-    const size_t bFirst = (size_t)blockIdx.y * bw + i0;
-    if (bFirst + nb <= blk0 || bFirst >= blk1) return;
-    const int cols = 8 * nb + 2 * R;
-    const int nPos = 8 * (nb - 1) + 2 * R + 1;
-
-    const uint8_t* wsrc = refPad + (intptr_t)by * strd + bx0;
-    for (int idx = tid; idx < WS * WROW; idx += NT) {
-        const int yy = idx / WROW, xx = idx - yy * WROW;
-        win[yy][xx] = xx < cols ? wsrc[(intptr_t)yy * strd + xx] : (uint8_t)0;
-    }
-    if (tid < S2_NB) sBest[tid] = ~0ull;
-    if (tid < nb * 8) {                              // horizontal transform of row (tid&7) of block (tid>>3)
-        const int i = tid >> 3, r = tid & 7;
-        int v[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) v[c] = cur[(size_t)(by + r) * w + bx0 + 8 * i + c];
-        had8<1>(v);
-#pragma unroll
-        for (int c = 0; c < 8; c++) tcur[i][r * 8 + c] = v[c];
-    }
-    __syncthreads();
-    if (tid < nb * 8) {                              // vertical transform of column (tid&7) of block (tid>>3)
-        const int i = tid >> 3, c = tid & 7;
-        int v[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) v[r] = tcur[i][r * 8 + c];
-        had8<1>(v);
-#pragma unroll
-        for (int r = 0; r < 8; r++) tcur[i][r * 8 + c] = v[r];
-    }
-    __syncthreads();
-
-    // From here on every warp runs on its own: it owns positions [32*warp, 32*warp+32) and computes the
-    // vertical transforms of the 39 window columns those positions touch (7 halo columns recomputed).
-    const int p = tid;
-    if (warp * 32 < nPos) {
-        int iLo = (p - 2 * R + 7) >> 3;
-        iLo = iLo < 0 ? 0 : iLo;
-        const int iHi = (p >> 3) < (nb - 1) ? (p >> 3) : (nb - 1);
-        // per-slot running best, 32-bit: cost << 7 | rank(my), rank orders dy by |dy| then sign (negative first);
-        // mx is fixed per slot, so this is the full tie-break rule restricted to the slot.
-        unsigned bestKey[SLOTS];
-#pragma unroll
-        for (int s = 0; s < SLOTS; s++) bestKey[s] = 0xFFFFFFFFu;
-        int (*Vw)[S2_VW] = V[warp];
-        const int c0 = warp * 32;
-
-        for (int my = 0; my < SIDE; my++) {
-            {
-                int v[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = win[my + i][c0 + lane];
-                had8<1>(v);
-#pragma unroll
-                for (int r = 0; r < 8; r++) Vw[r][lane] = v[r];
-                if (lane < 7) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) v[i] = win[my + i][c0 + 32 + lane];
-                    had8<1>(v);
-#pragma unroll
-                    for (int r = 0; r < 8; r++) Vw[r][32 + lane] = v[r];
-                }
-            }
-            __syncwarp();
-            if (p < nPos) {
-                int T[64];
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) T[r * 8 + c] = Vw[r][lane + c];
-                    had8<1>(&T[r * 8]);
-                }
-                const int dy = my - R;
-                const unsigned rank = dy < 0 ? (unsigned)(-2 * dy - 1) : (unsigned)(2 * dy);
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    const int i = iLo + s;
-                    if (i <= iHi) {
-                        const int4* tc = reinterpret_cast<const int4*>(&tcur[i][0]);
-                        unsigned sa = 0, sb = 0, sc = 0, sd = 0;       // 4 independent chains (VABSDIFF latency)
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const int4 c = tc[k];
-                            sa = __sad(T[4 * k + 0], c.x, sa);
-                            sb = __sad(T[4 * k + 1], c.y, sb);
-                            sc = __sad(T[4 * k + 2], c.z, sc);
-                            sd = __sad(T[4 * k + 3], c.w, sd);
-                        }
-                        const unsigned c4 = ((sa + sb) + (sc + sd) + 2) >> 2;
-                        const size_t b = bFirst + i;
-                        if (b >= blk0 && b < blk1) {
-                            if (cost) cost[((b - blk0) * SIDE + my) * SIDE + (p - 8 * i)] = c4;
-                            const unsigned key = (c4 << 7) | rank;
-                            bestKey[s] = key < bestKey[s] ? key : bestKey[s];
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        if (best && p < nPos) {
-#pragma unroll
-            for (int s = 0; s < SLOTS; s++) {
-                const int i = iLo + s;
-                if (i <= iHi && bestKey[s] != 0xFFFFFFFFu) {
-                    const unsigned rank = bestKey[s] & 127u;
-                    const int dy = (rank & 1) ? -(int)((rank + 1) >> 1) : (int)(rank >> 1);
-                    const int mx = p - 8 * i, dx = mx - R, my = dy + R;
-                    const unsigned long long key = ((unsigned long long)(bestKey[s] >> 7) << 40) |
-                                                   ((unsigned long long)(dx * dx + dy * dy) << 24) |
-                                                   ((unsigned long long)my << 12) | (unsigned long long)mx;
-                    atomicMin(&sBest[i], key);
-                }
-            }
-        }
-    }
-    if (best) {
-        __syncthreads();
-        if (tid < nb) {
-            const size_t b = bFirst + tid;
-            if (b >= blk0 && b < blk1) {
-                const unsigned long long k = sBest[tid];
-                int32_t* o = best + (b - blk0) * 3;
-                o[0] = (int32_t)(k >> 40);
-                o[1] = (int)(k & 0xFFF) - R;
-                o[2] = (int)((k >> 12) & 0xFFF) - R;
-            }
-        }
-    }
-}
-
-static std::atomic<int> g_searchV1{0};      // 0: v3 (satd_search3.cu); 1: v1; 2: v2 squeezed to 3 CTAs/SM; 3: v2, 2 CTAs/SM
+static std::atomic<int> g_searchV1{0};      // 0: v3 (satd_search3.cu) for R in {8, 16, 32}; 1: the any-range kernel (one CTA per block) for every R
 void set_search_v1(int on) { g_searchV1 = on; }
-
-template <int R>
-static cudaError_t launch_search_v2(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h,
-                                    size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
-{
-    const int bw = w / 8, bh = h / 8;
-    const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
-    (void)bh;
-    // grid.y starts at block-row 0; CTAs outside [blk0, blk1) exit immediately
-    dim3 grid((bw + S2_NB - 1) / S2_NB, y1 + 1);
-    (void)y0;
-    constexpr int NT = ((8 * S2_NB + 2 * R + 31) / 32) * 32;
-    if (g_searchV1 == 2) satd8x8_search_v2_kernel<R, 3><<<grid, NT, 0, st>>>(cur, refPad, strd, w, blk0, blk1, cost, best);
-    else satd8x8_search_v2_kernel<R, 2><<<grid, NT, 0, st>>>(cur, refPad, strd, w, blk0, blk1, cost, best);
-    count_launch();
-    return cudaGetLastError();
-}
 
 // ------------------------------------------------------------------------------------------------
 // Batch on the tensor cores, v2 (shipped): H64 = H2 (x) H32.  The butterfly on sample-index bit 5 pairs sample p
@@ -545,95 +267,10 @@ __device__ __forceinline__ uint32_t vadd16x2(uint32_t a, uint32_t b)
     return r;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(SATDI_WARPS * 32, MINB)
-satd8x8_imma2_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, q = lane & 3;
-
-    // H32 fragments: K position 16r+4q+i <-> sample 8q+4r+i (of the 32 folded samples), column n' = 8t+g
-    uint32_t B[4][2];
-#pragma unroll
-    for (int t = 0; t < 4; t++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int pix = 8 * q + 4 * r + i, nn = 8 * t + g;
-                v |= ((__popc(nn & pix) & 1) ? 0xFFu : 0x01u) << (8 * i);
-            }
-            B[t][r] = v;
-        }
-    const int cZero[4] = { 0, 0, 0, 0 };
-    // +32 on bottom-half coefficient 0 (tile 0, column 0 = lanes with q == 0, accumulator slots 0 and 2)
-    const int cFix[4] = { q == 0 ? 32 : 0, 0, q == 0 ? 32 : 0, 0 };
-
-    const size_t nUnits = (n + 15) / 16;
-    const size_t first = (size_t)blockIdx.x * SATDI_WARPS + warp;
-    const size_t stride = (size_t)gridDim.x * SATDI_WARPS;
-
-    auto load_unit = [&](size_t u, uint4 (&w)[2][2]) {
-        size_t c0 = u * 16 + g, c1 = c0 + 8;
-        c0 = c0 < n ? c0 : n - 1;
-        c1 = c1 < n ? c1 : n - 1;
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            w[s][0] = ld_global_nc(diff + c0 * 64 + 32 * s + 8 * q);
-            w[s][1] = ld_global_nc(diff + c1 * 64 + 32 * s + 8 * q);
-        }
-    };
-
-    uint4 nxt[2][2] = {};
-    if (first < nUnits) load_unit(first, nxt);
-
-    for (size_t u = first; u < nUnits; u += stride) {
-        // fold bit 5, then byte planes.  Fragment registers: [0] row g K 4q+i, [1] row g+8, [2] row g K 16+4q+i, [3] row g+8
-        uint32_t TL[4], TH[4], BLo[4], BHi[4];
-#pragma unroll
-        for (int row = 0; row < 2; row++) {
-            const uint4 a = nxt[0][row], b = nxt[1][row];
-            const uint32_t tx = vadd16x2(a.x, b.x), ty = vadd16x2(a.y, b.y), tz = vadd16x2(a.z, b.z), tw = vadd16x2(a.w, b.w);
-            const uint32_t bx = vadd16x2(a.x, ~b.x), by = vadd16x2(a.y, ~b.y), bz = vadd16x2(a.z, ~b.z), bw = vadd16x2(a.w, ~b.w);
-            TL[row] = prmt(tx, ty, 0x6420);      TH[row] = prmt(tx, ty, 0x7531);
-            TL[2 + row] = prmt(tz, tw, 0x6420);  TH[2 + row] = prmt(tz, tw, 0x7531);
-            BLo[row] = prmt(bx, by, 0x6420);     BHi[row] = prmt(bx, by, 0x7531);
-            BLo[2 + row] = prmt(bz, bw, 0x6420); BHi[2 + row] = prmt(bz, bw, 0x7531);
-        }
-        if (u + stride < nUnits) load_unit(u + stride, nxt);
-
-        unsigned s0a = 0, s0b = 0, s1a = 0, s1b = 0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            int dl[4], dh[4], el[4], eh[4];
-            mma_u8s8(dl, TL, B[t][0], B[t][1], cZero);
-            mma_s8s8(dh, TH, B[t][0], B[t][1], cZero);
-            if (t == 0) mma_u8s8(el, BLo, B[t][0], B[t][1], cFix);
-            else mma_u8s8(el, BLo, B[t][0], B[t][1], cZero);
-            mma_s8s8(eh, BHi, B[t][0], B[t][1], cZero);
-            // lo + 256*hi (IMAD); the int16 coefficient is the low half (= the reference's wrap, satd.c:35).  Two coefficients are packed
-            // into one word and |.| is max(x, -x) on both halves (LOP3 + VIADDMNMX.S16x2; -32768 stays 0x8000 = 32768 unsigned, as
-            // abs() of the widened value gives in C); IDP.2A adds the two unsigned halves to the accumulator on the FMA pipe:
-            // 3 ALU + 3 FMA instructions per coefficient pair instead of 4 + 2 -- the ALU pipe is the busier one here.
-            auto abs2 = [](int lo0, int hi0, int lo1, int hi1, unsigned acc) {
-                const uint32_t x = prmt((uint32_t)(lo0 + hi0 * 256), (uint32_t)(lo1 + hi1 * 256), 0x5410);
-                return __dp2a_lo(__vmaxs2(x, __vneg2(x)), 0x0101u, acc);
-            };
-            s0a = abs2(dl[0], dh[0], dl[1], dh[1], s0a); s1a = abs2(dl[2], dh[2], dl[3], dh[3], s1a);
-            s0b = abs2(el[0], eh[0], el[1], eh[1], s0b); s1b = abs2(el[2], eh[2], el[3], eh[3], s1b);
-        }
-        unsigned sad0 = s0a + s0b, sad1 = s1a + s1b;
-        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 1); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 1);
-        sad0 += __shfl_xor_sync(0xffffffffu, sad0, 2); sad1 += __shfl_xor_sync(0xffffffffu, sad1, 2);
-        if (q == 0) {
-            const size_t c0 = u * 16 + g;
-            if (c0 < n) out[c0] = (int)((sad0 + 2) >> 2);
-            if (c0 + 8 < n) out[c0 + 8] = (int)((sad1 + 2) >> 2);
-        }
-    }
-}
-
+// HBM staging: this stream is 97 % reads, and reads must be covered by bytes in flight.  The 2 KiB units (16 candidates) arrive through a per-warp
+// ring of ST stages filled by per-lane 16-byte asynchronous copies (cp.async.cg, SASS LDGSTS): every lane reads back only the chunks it copied
+// itself, so completion needs nothing but cp.async.wait_group, and (ST - 1) x 2 KiB per warp are in flight at no register cost
+// (register double-buffering: 0.91 of the copy roofline, this ring: 0.94-0.99; profiles/r01_time_satd.log).
 template <int MINB, int ST>
 __global__ void __launch_bounds__(SATDI_WARPS * 32, MINB)
 satd8x8_imma3_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out, size_t n)
@@ -739,8 +376,7 @@ satd8x8_imma3_kernel(const int16_t* __restrict__ diff, int32_t* __restrict__ out
     }
 }
 
-static std::atomic<int> g_satdCuda{0};      // tuning/diagnostic: 0 = IMMA v2 fed by a 3-stage cp.async ring (shipped), 1 = CUDA-core kernel, 2 = IMMA v1 (32 IMMA per unit),
-                                // 3 = IMMA v2 register double-buffered at 3 CTAs/SM, 4 = the same at 2 CTAs/SM, 5 = ring with 4 stages
+static std::atomic<int> g_satdCuda{0};      // tuning/diagnostic: 0 = tensor cores, H2 (x) H32 fold, 3-stage cp.async ring (shipped), 1 = CUDA-core kernel, 5 = 4-stage ring
 void set_satd_cuda_cores(int on) { g_satdCuda = on; }
 
 cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cudaStream_t st)
@@ -748,24 +384,19 @@ cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cu
     if (n == 0) return cudaSuccess;
     if (g_satdCuda != 1) {
         size_t want = ((n + 15) / 16 + SATDI_WARPS - 1) / SATDI_WARPS;
-        size_t cap = (size_t)sm_count() * (g_satdCuda == 3 ? 3 : 2);
+        size_t cap = (size_t)sm_count() * 2;
         const int grid = (int)(want < cap ? want : cap);
-        if (g_satdCuda == 0 || g_satdCuda == 5) {                 // shipped: cp.async ring, 3 stages (5: 4 stages)
-            constexpr int smem3 = SATDI_WARPS * 3 * 2048, smem4 = SATDI_WARPS * 4 * 2048;
-            static std::atomic<bool> attrSet4[64];
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (g_satdCuda == 5 && (dev < 0 || dev >= 64 || !attrSet4[dev])) {
-                cudaError_t e = cudaFuncSetAttribute(satd8x8_imma3_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
-                if (e != cudaSuccess) return e;
-                if (dev >= 0 && dev < 64) attrSet4[dev] = true;
-            }
-            if (g_satdCuda == 5) satd8x8_imma3_kernel<2, 4><<<grid, SATDI_WARPS * 32, smem4, st>>>(diff, out, n);
-            else satd8x8_imma3_kernel<2, 3><<<grid, SATDI_WARPS * 32, smem3, st>>>(diff, out, n);
+        constexpr int smem3 = SATDI_WARPS * 3 * 2048, smem4 = SATDI_WARPS * 4 * 2048;
+        static std::atomic<bool> attrSet4[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (g_satdCuda == 5 && (dev < 0 || dev >= 64 || !attrSet4[dev])) {
+            cudaError_t e = cudaFuncSetAttribute(satd8x8_imma3_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attrSet4[dev] = true;
         }
-        else if (g_satdCuda == 2) satd8x8_imma_kernel<2, 1><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
-        else if (g_satdCuda == 3) satd8x8_imma2_kernel<3><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
-        else satd8x8_imma2_kernel<2><<<grid, SATDI_WARPS * 32, 0, st>>>(diff, out, n);
+        if (g_satdCuda == 5) satd8x8_imma3_kernel<2, 4><<<grid, SATDI_WARPS * 32, smem4, st>>>(diff, out, n);
+        else satd8x8_imma3_kernel<2, 3><<<grid, SATDI_WARPS * 32, smem3, st>>>(diff, out, n);
         count_launch();
         return cudaGetLastError();
     }
@@ -791,11 +422,6 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
     if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
     if (g_searchV1 == 0 && (range == 32 || range == 16 || range == 8))
         return launch_satd8x8_search_v3(cur, refPad, strd, w, h, range, blk0, blk1, cost, best, st);
-    if (g_searchV1 != 1) {
-        if (range == 32) return launch_search_v2<32>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
-        if (range == 16) return launch_search_v2<16>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
-        if (range == 8) return launch_search_v2<8>(cur, refPad, strd, w, h, blk0, blk1, cost, best, st);
-    }
     const int ws = 2 * range + 8, wsp = (ws + 3) & ~3;
     const size_t smem = 128 * sizeof(int) + (size_t)SRCH_WARPS * 8 * wsp * sizeof(int) + (size_t)ws * wsp;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
