@@ -676,7 +676,7 @@ def e2e_dct32(env, src, dst):
         env.host_barrier()
         if env.rank == 0:
             try:
-                per = max(4, frames // 4)
+                per = max(4, frames // 2)
                 tot = world * per * BLOCKS_PER_FRAME
                 big_in = env.pinned((tot, 32, 32), torch.int16)
                 big_out = env.pinned((tot, 32, 32), torch.int16)

@@ -311,7 +311,8 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 struct ChunkClaimer {
     std::atomic<size_t> next{0};
     size_t nUnits = 0, chunk = 0;
-    ChunkClaimer(size_t n, size_t c) : nUnits(n), chunk(c) {}
+    bool shared = false;               // several pipelines claim from this counter: each may only claim when one of its slots is free
+    ChunkClaimer(size_t n, size_t c, bool sh = false) : nUnits(n), chunk(c), shared(sh) {}
     bool claim(size_t* u0, size_t* nu)
     {
         const size_t at = next.fetch_add(chunk, std::memory_order_relaxed);
@@ -353,8 +354,12 @@ static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* o
     struct Fly { size_t u0, nu; int s; };
     Fly fly[SLOTS];                                          // staged chunks enqueued but not yet copied out to the caller, oldest first
     int nFly = 0;
+    const bool track = anyStOut || claimer.shared;           // an event per slot marks "this slot's chunk is back on the host"
     for (size_t i = 0;; ) {
         size_t u0 = 0, nu = 0;
+        // Shared counter: enqueueing is asynchronous, so without back-pressure the first thread to run would claim every chunk.  A pipeline
+        // claims its next chunk only once the slot that chunk will use has drained -- a GPU behind a slower link drains, and so claims, less often.
+        if (claimer.shared && i >= SLOTS) CK(cudaEventSynchronize(p.evOut[i % SLOTS]));
         const bool got = claimer.claim(&u0, &nu);
         if (!got && nFly == 0) break;
         const int s = (int)(i % SLOTS);
@@ -396,10 +401,8 @@ static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* o
             void* to = stOut[k] ? (void*)((char*)p.pOut[s] + offOut[k]) : (void*)((char*)outs[k].h + u0 * outs[k].unit);
             CK(cudaMemcpyAsync(to, dO[k], nu * outs[k].unit, cudaMemcpyDeviceToHost, p.st[s]));
         }
-        if (anyStOut) {
-            CK(cudaEventRecord(p.evOut[s], p.st[s]));
-            fly[nFly++] = Fly{ u0, nu, s };                   // nFly <= LAG < SLOTS here: the slot about to be reused is never in flight
-        }
+        if (track) CK(cudaEventRecord(p.evOut[s], p.st[s]));
+        if (anyStOut) fly[nFly++] = Fly{ u0, nu, s };         // nFly <= LAG < SLOTS here: the slot about to be reused is never in flight
         i++;
     }
     for (int s = 0; s < SLOTS; s++) CK(cudaStreamSynchronize(p.st[s]));
@@ -606,7 +609,7 @@ extern "C" int xDct32BatchMultiGpu(const int16_t* src, int16_t* dst, size_t nBlo
     CK(cudaGetDevice(&prev));
     // chunks small enough that every GPU gets several, large enough to amortise the hand-over
     size_t chunk = dct32_chunk(nBlocks / nGpus + 1);
-    ChunkClaimer claimer(nBlocks, chunk < nBlocks ? chunk : nBlocks);
+    ChunkClaimer claimer(nBlocks, chunk < nBlocks ? chunk : nBlocks, /*shared*/ true);
     const HostArr in{ const_cast<int16_t*>(src), 2048 }, out{ dst, 2048 };
     std::vector<int> rc(nGpus, 0);
     std::vector<std::string> err(nGpus);
