@@ -27,10 +27,10 @@ if os.path.exists(src):
         a[0] += 1; a[1] += v
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(P, f"{tag}_launch_list_bench.md"), "w") as f:
-        f.write("# ncu launch list of `python bench.py --steps 5 --warmup 3` (gpu__time_duration.sum, --clock-control none, first 400 launches)\n\n"
+        f.write("# ncu launch list of `python bench.py --steps 5 --warmup 3 --no-secondary` (gpu__time_duration.sum, --clock-control none, first 800 launches)\n\n"
                 "Per-launch times are cold-cache and serialised under the profiler: compare shares, not absolutes. `dct32_imma_kernel` launches are the "
-                "warm-up, the timed steps (2 073 600 blocks each) and the chunks of the e2e host-pointer path; `at::` kernels are torch generating the "
-                "synthetic inputs outside any timed region.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+                "warm-up, the timed steps (2 073 600 blocks each) and the chunks of the e2e host-pointer paths (pinned, pageable, registered); `at::` kernels are "
+                "torch generating the synthetic inputs and the link-ceiling probe outside any timed region.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
         for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{name}` | {n} | {ms:.3f} | {100 * ms / tot:.1f}% |\n")
 

@@ -44,5 +44,23 @@ xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c
 xb.tune(1, 0)
 for _ in range(2):
     xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+# round 2: inverse, fused residual + DCT32 on tiled frames, mode-major predictor, decision, the closed block loop and its Recon leg, quantiser stub
+xb.xIdct32BatchDev(src.data_ptr(), dst.data_ptr(), n, 7, 12, st)
+fw, fh = 7680, 4320 * 2 // 32 * 32
+nt = (fw // 16) * (fh // 16)
+ct = torch.randint(0, 256, (nt * 512,), device=dev, dtype=torch.uint8)
+pt = torch.randint(0, 256, (nt * 512,), device=dev, dtype=torch.uint8)
+xb.xFrameResiDct32Dev(ct.data_ptr(), pt.data_ptr(), fw, fh, dst.data_ptr(), 4, 11, st)
+xb.xIntra32PredModesDev(refs.data_ptr(), npred // 35, (1 << 35) - 1, pred.data_ptr(), st)
+nblk = 32400
+ecur = torch.randint(0, 256, (nblk, 1024), device=dev, dtype=torch.uint8)
+ecost = torch.empty((nblk, 35), device=dev, dtype=torch.int32)
+ebest = torch.empty(nblk, device=dev, dtype=torch.int32)
+elev = torch.empty((nblk, 1024), device=dev, dtype=torch.int16)
+erec = torch.empty((nblk, 1024), device=dev, dtype=torch.uint8)
+xb.xIntra32DecideDev(ecur.data_ptr(), refs.data_ptr(), ecost.data_ptr(), ebest.data_ptr(), nblk, st)
+xb.xIntra32EncodeBlockDev(ecur.data_ptr(), refs.data_ptr(), nblk, 27, elev.data_ptr(), erec.data_ptr(), ebest.data_ptr(), 0, st)
+xb.xIntra32ReconDev(ecur.data_ptr(), refs.data_ptr(), ebest.to(torch.uint8).data_ptr(), nblk, 27, elev.data_ptr(), erec.data_ptr(), st)
+xb.xQuantDequantDev(src.data_ptr(), dst.data_ptr(), 0, n * 1024, 27, st)
 torch.cuda.synchronize()
 print("profile driver done")
