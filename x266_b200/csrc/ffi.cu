@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "hostcopy.h"
+#include "chunk_claimer.h"
 
 #include <atomic>
 #include <condition_variable>
@@ -305,24 +306,6 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 //     between runs underneath.  (xGpuTune 12 selects the two alternatives that were measured against it.)
 // launch(dIn[k], dOut[k], first unit, units, stream) enqueues the kernel(s) of one chunk.
 // ------------------------------------------------------------------------------------------------
-// Where the next chunk of a call comes from.  A single-GPU call walks its range in order; the multi-GPU entry point shares ONE
-// claimer between its per-device threads, so a GPU with a slower host link simply claims fewer chunks (the links of one box are
-// not equal: profiles/r02_link_ceiling.md).
-struct ChunkClaimer {
-    std::atomic<size_t> next{0};
-    size_t nUnits = 0, chunk = 0;
-    bool shared = false;               // several pipelines claim from this counter: each may only claim when one of its slots is free
-    ChunkClaimer(size_t n, size_t c, bool sh = false) : nUnits(n), chunk(c), shared(sh) {}
-    bool claim(size_t* u0, size_t* nu)
-    {
-        const size_t at = next.fetch_add(chunk, std::memory_order_relaxed);
-        if (at >= nUnits) return false;
-        *u0 = at;
-        *nu = (nUnits - at) < chunk ? (nUnits - at) : chunk;
-        return true;
-    }
-};
-
 template <typename Launch>
 static int run_chunked_on(Pipe& p, const HostArr* ins, int nIn, const HostArr* outs, int nOut, ChunkClaimer& claimer, Launch launch)
 {
