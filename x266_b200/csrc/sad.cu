@@ -174,6 +174,13 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
     }
 
     const int sh = (xa & 3) * 8;
+    uint32_t slotMask = 0;                       // this lane's slots that are real blocks inside [blk0, blk1): independent of the vertical offset
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+        const int i = iq + s;
+        const size_t b = bRow + i;
+        if (i >= 0 && i < bw && b >= blk0 && b < blk1) slotMask |= 1u << s;
+    }
     for (int my = my0; my < my1; my++) {
         uint32_t A[16], B[16];
 #pragma unroll
@@ -188,9 +195,7 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
         uint32_t* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) {
-            const int i = iq + s;
-            const size_t b = bRow + i;
-            if (i >= 0 && i < bw && b >= blk0 && b < blk1) {
+            if ((slotMask >> s) & 1u) {
                 const bool doA = (s <= R / 4) && (s >= 1 || e == 0);
                 const bool doB = (s >= 1) && (s >= 2 || e == 0);
                 const uint4* cp = reinterpret_cast<const uint4*>(&curs[(2 * g + s) * SAD2_CS]);
@@ -210,14 +215,12 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
                 if (doA) {
                     const unsigned v = a0 + a1;
                     if (cost) cbase[s * (SIDE * SIDE - 8)] = v;
-                    const unsigned key = (v << 7) | rank;
-                    keyA[s] = key < keyA[s] ? key : keyA[s];
+                    keyA[s] = min(v * 128u + rank, keyA[s]);          // key as a multiply-add (FMA pipe); the ALU pipe is this kernel's limiter
                 }
                 if (doB) {
                     const unsigned v = b0 + b1;
                     if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = v;
-                    const unsigned key = (v << 7) | rank;
-                    keyB[s] = key < keyB[s] ? key : keyB[s];
+                    keyB[s] = min(v * 128u + rank, keyB[s]);
                 }
             }
         }

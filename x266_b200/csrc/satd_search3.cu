@@ -134,6 +134,14 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
         }
     }
 
+    // which of this lane's slots are real blocks inside [blk0, blk1): does not depend on the vertical offset
+    uint32_t slotMask = 0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+        const int i = iq + s;
+        const size_t b = bRow + i;
+        if (i >= 0 && i < bw && b >= blk0 && b < blk1) slotMask |= 1u << s;
+    }
     for (int my = my0; my < my1; my++) {
         const uint8_t* wrow = win + (my - my0) * S3_WP;      // window row of this vertical offset
         // ---- one vertical offset: vertical pass of the 72 window columns, then the two positions of this lane
@@ -167,9 +175,7 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
 
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) {
-            const int i = iq + s;
-            const size_t b = bRow + i;
-            if (i >= 0 && i < bw && b >= blk0 && b < blk1) {
+            if ((slotMask >> s) & 1u) {
                 const bool doA = (s <= R / 4) && (s >= 1 || e == 0);
                 const bool doB = (s >= 1) && (s >= 2 || e == 0);
                 const uint32_t* tc = tcur[2 * g + s];
@@ -181,17 +187,17 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
                     if (s >= 1) accB = s3::maxsum4<ACCF>(&TB[4 * k], c.x, c.y, c.z, c.w, accB);
                 }
                 const uint32_t c64 = tc[32];
+                // the tail of a candidate on the FMA pipe: x >> 2 as the high word of x * 2^30, key = cost * 128 + rank as a multiply-add;
+                // only the running minimum needs the integer ALU pipe (the limiter of this kernel)
                 if (doA) {
-                    const uint32_t c4 = (2u * accA - subA - c64) >> 2;
+                    const uint32_t c4 = __umulhi(2u * accA - subA - c64, 1u << 30);
                     if (cost) cbase[s * (SIDE * SIDE - 8)] = c4;
-                    const unsigned key = (c4 << 7) | rank;
-                    keyA[s] = key < keyA[s] ? key : keyA[s];
+                    keyA[s] = min(c4 * 128u + rank, keyA[s]);
                 }
                 if (doB) {
-                    const uint32_t c4 = (2u * accB - subB - c64) >> 2;
+                    const uint32_t c4 = __umulhi(2u * accB - subB - c64, 1u << 30);
                     if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = c4;
-                    const unsigned key = (c4 << 7) | rank;
-                    keyB[s] = key < keyB[s] ? key : keyB[s];
+                    keyB[s] = min(c4 * 128u + rank, keyB[s]);
                 }
             }
         }
