@@ -156,6 +156,18 @@ int xSad8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, i
 int xSad8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
                      size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream);
 
+/* The same searches with a 16-bit cost surface, cost[(b-blk0)][my][mx] as uint16_t -- exact, because an 8x8 SATD of 8-bit pixels cannot
+ * exceed 32640 (sum |T_k| <= 8 ||T||_2 = 64 ||x||_2 <= 130560 before the >> 2 of src_tb/satd.c:113) and an 8x8 SAD cannot exceed 16320.
+ * Halves the bytes of the surface (547.6 -> 273.8 MB per 1080p +-32 frame), which is all but 4 MB of the searches' HBM and host-link traffic. */
+int xSatd8x8SearchU16(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                      size_t blk0, size_t blk1, uint16_t* cost, int32_t* best);
+int xSatd8x8SearchU16Dev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                         size_t blk0, size_t blk1, uint16_t* dCost, int32_t* dBest, void* stream);
+int xSad8x8SearchU16(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                     size_t blk0, size_t blk1, uint16_t* cost, int32_t* best);
+int xSad8x8SearchU16Dev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                        size_t blk0, size_t blk1, uint16_t* dCost, int32_t* dBest, void* stream);
+
 /* 32x32 intra prediction (src/mkIntra32-wip.bsv:34-48,61-397): n predictions; refs[i] = 64 left
  * pixels then 65 top pixels (corner first) = 129 bytes; mode[i] in 0..34 (0 planar, 1 DC, 2..34
  * angular); pred[i] = 32x32 u8 row-major. */
@@ -237,6 +249,11 @@ int xSatd8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int wid
                            uint32_t* dCost, int32_t* dBest, void* stream);
 int xSad8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
                           uint32_t* dCost, int32_t* dBest, void* stream);
+/* 16-bit cost surface (see xSatd8x8SearchU16) */
+int xSatd8x8SearchTiledU16Dev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                              uint16_t* dCost, int32_t* dBest, void* stream);
+int xSad8x8SearchTiledU16Dev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                             uint16_t* dCost, int32_t* dBest, void* stream);
 
 /* Fused residual + transform for the block loop of xEncodeFrame (src/x266.cpp:537-546): for every 32x32 luma
  * block b (raster order, width and height multiples of 32) of the tiled frames cur and pred,

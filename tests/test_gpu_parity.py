@@ -237,8 +237,16 @@ def test_satd_search_small(x266, orc, rng_px, v1):
     assert np.array_equal(best, wb)
 
 
-@pytest.mark.parametrize("rng_px", [8, 32])
-def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px):
+@pytest.fixture(params=[0, 1, 2])
+def search_var(request, x266):
+    """loop structure of the v3 SATD search (xGpuTune 17; satd_search3.cu VAR)"""
+    x266.tune(17, request.param)
+    yield request.param
+    x266.tune(17, 0)
+
+
+@pytest.mark.parametrize("rng_px", [8, 16, 32])
+def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px, search_var):
     """width 200 = one full strip of 16 blocks + a ragged strip of 9; block sub-ranges that start and end
     mid-strip / mid-row; extreme flat frames (all ties -> the tie-break rule decides)."""
     cur, refp = make_frames(200, 24, rng_px, seed=5)
@@ -258,7 +266,7 @@ def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px):
 
 
 @pytest.mark.parametrize("rng_px", [8, 16, 32])
-def test_satd_search_extreme_patterns(x266, orc, rng_px):
+def test_satd_search_extreme_patterns(x266, orc, rng_px, search_var):
     """v3 keeps two biased coefficients per 32-bit word: frames built from the 64 Hadamard basis patterns (pixels
     0/255, every coefficient driven to +-8160 / 16320) and from random 0/255 pixels must not carry between halves."""
     r = np.random.default_rng(11)
@@ -559,6 +567,53 @@ def test_sad_search_wide_frame_and_ties(x266, orc, rng_px):
     flatp = np.full((24 + 2 * rng_px, 200 + 2 * rng_px), 10, np.uint8)
     c, b = x266.xSad8x8Search(flat, flatp, rng_px)
     assert (b[:, 1] == 0).all() and (b[:, 2] == 0).all() and (c == 64 * 190).all()
+
+
+@pytest.mark.parametrize("rng_px", [3, 8, 32])
+def test_search_u16_cost_surface(x266, orc, rng_px):
+    """xSatd8x8SearchU16 / xSad8x8SearchU16 (+Dev, +TiledDev): the same costs as 16-bit words -- exact, since an 8x8 SATD of 8-bit pixels is
+    <= 32640 and a SAD <= 16320; the all-0 vs all-255 frame reaches the SAD maximum and the largest SATD DC"""
+    import torch
+    cur, refp = make_frames(72, 40, rng_px, seed=11)
+    for fn, oracle in ((x266.xSatd8x8Search, orc.satd_search), (x266.xSad8x8Search, orc.sad_search)):
+        wc, wb = oracle(cur, refp, rng_px, 0, 45)
+        c, b = fn(cur, refp, rng_px, u16=True)
+        assert c.dtype == np.uint16 and np.array_equal(c, wc) and np.array_equal(b, wb)
+        c, b = fn(cur, refp, rng_px, 7, 20, u16=True)
+        assert np.array_equal(c, wc[7:20]) and np.array_equal(b, wb[7:20])
+    zero = np.zeros((16, 32), np.uint8)
+    full = np.full((16 + 2 * rng_px, 32 + 2 * rng_px), 255, np.uint8)
+    c, _ = x266.xSad8x8Search(zero, full, rng_px, u16=True)
+    assert (c == 16320).all()
+    c, _ = x266.xSatd8x8Search(zero, full, rng_px, u16=True)
+    assert (c == 4080).all()
+    # device forms, misaligned cost pointer (2-byte aligned only), and the tiled device forms
+    w, h = 72, 40
+    side, nb = 2 * rng_px + 1, 45
+    dcur, dref = torch.from_numpy(cur).cuda(), torch.from_numpy(refp).cuda()
+    for fn, oracle in ((x266.xSatd8x8SearchU16Dev, orc.satd_search), (x266.xSad8x8SearchU16Dev, orc.sad_search)):
+        buf = torch.zeros(nb * side * side + 1, dtype=torch.int16, device="cuda")
+        dbest = torch.empty((nb, 3), dtype=torch.int32, device="cuda")
+        fn(dcur.data_ptr(), dref.data_ptr(), refp.shape[1], w, h, rng_px, 0, nb, buf.data_ptr() + 2, dbest.data_ptr())
+        torch.cuda.synchronize()
+        wc, wb = oracle(cur, refp, rng_px, 0, nb)
+        assert np.array_equal(buf[1:].cpu().numpy().view(np.uint16).reshape(nb, side, side), wc)
+        assert np.array_equal(dbest.cpu().numpy(), wb)
+    if rng_px == 8:
+        w, h = 48, 32
+        cur = np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8)
+        ref = np.random.default_rng(h).integers(0, 256, (h, w), dtype=np.uint8)
+        refp = np.pad(ref, rng_px, mode="edge")
+        zc = np.zeros((h // 2, w // 2), np.uint8)
+        dct, drt = (torch.from_numpy(orc.conv_input_fmt(p, zc, zc)).cuda() for p in (cur, ref))
+        nb = (w // 8) * (h // 8)
+        for fn, oracle in ((x266.xSatd8x8SearchTiledU16Dev, orc.satd_search), (x266.xSad8x8SearchTiledU16Dev, orc.sad_search)):
+            dcost = torch.zeros((nb, side, side), dtype=torch.int16, device="cuda")
+            dbest = torch.empty((nb, 3), dtype=torch.int32, device="cuda")
+            fn(dct.data_ptr(), drt.data_ptr(), w, h, rng_px, 0, nb, dcost.data_ptr(), dbest.data_ptr())
+            torch.cuda.synchronize()
+            wc, wb = oracle(cur, refp, rng_px, 0, nb)
+            assert np.array_equal(dcost.cpu().numpy().view(np.uint16), wc) and np.array_equal(dbest.cpu().numpy(), wb)
 
 
 # ------------------------------------------------------------------ fused intra mode decision ("next" N1)

@@ -15,5 +15,6 @@ from .binding import (  # noqa: F401
     xTranspose32x32Batch, xTranspose32x32BatchDev,
     xIntra32Decide, xIntra32DecideDev, xIntra32PredModes, xIntra32PredModesDev, xIntra32EncodeBlock, xIntra32EncodeBlockDev, xIntra32Recon, xIntra32ReconDev, xQuantDequantDev, xIdct32Batch, xIdct32BatchDev, xDct32BatchMultiGpu,
     sad, xSad8x8Search, xSad8x8SearchDev, xIntra32MmaTable,
+    xSad8x8SearchU16Dev, xSatd8x8SearchU16Dev, xSatd8x8SearchTiledU16Dev, xSad8x8SearchTiledU16Dev,
     bdpi_dct_block, bdpi_satd_block, X266Error,
 )

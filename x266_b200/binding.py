@@ -98,6 +98,11 @@ def lib():
     _set(L, "sad", "restype", i)
     _set(L, "xSad8x8Search", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp])
     _set(L, "xSad8x8SearchDev", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp])
+    for nm in ("xSatd8x8SearchU16", "xSad8x8SearchU16"):
+        _set(L, nm, "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp])
+        _set(L, nm + "Dev", "argtypes", [vp, vp, C.c_ssize_t, i, i, i, sz, sz, vp, vp, vp])
+    _set(L, "xSatd8x8SearchTiledU16Dev", "argtypes", [vp, vp, i, i, i, sz, sz, vp, vp, vp])
+    _set(L, "xSad8x8SearchTiledU16Dev", "argtypes", [vp, vp, i, i, i, sz, sz, vp, vp, vp])
     _set(L, "partialButterfly32", "argtypes", [vp, vp, i, i])
     _set(L, "partialButterfly32", "restype", None)
     _set(L, "satd8x8", "argtypes", [vp])
@@ -219,7 +224,8 @@ def xSatd8x8Batch(diff):
     return out
 
 
-def xSatd8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want_best=True):
+def xSatd8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want_best=True, u16=False):
+    """u16=True: xSatd8x8SearchU16 (16-bit cost surface)"""
     cur = _np(cur, np.uint8)
     ref_padded = _np(ref_padded, np.uint8)
     h, w = cur.shape
@@ -228,11 +234,12 @@ def xSatd8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want
         blk1 = (w // 8) * (h // 8)
     side = 2 * rng + 1
     nb = blk1 - blk0
-    cost = np.empty((nb, side, side), np.uint32) if want_cost else None
+    cost = np.empty((nb, side, side), np.uint16 if u16 else np.uint32) if want_cost else None
     best = np.empty((nb, 3), np.int32) if want_best else None
-    _ck(lib().xSatd8x8Search(cur.ctypes.data, ref_padded.ctypes.data, ref_padded.shape[1], w, h, rng, blk0, blk1,
-                             cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None),
-        "xSatd8x8Search")
+    fn = lib().xSatd8x8SearchU16 if u16 else lib().xSatd8x8Search
+    _ck(fn(cur.ctypes.data, ref_padded.ctypes.data, ref_padded.shape[1], w, h, rng, blk0, blk1,
+           cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None),
+        "xSatd8x8SearchU16" if u16 else "xSatd8x8Search")
     return cost, best
 
 
@@ -322,7 +329,8 @@ def sad(a, b):
     return int(lib().sad(a.ctypes.data, b.ctypes.data, n))
 
 
-def xSad8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want_best=True):
+def xSad8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want_best=True, u16=False):
+    """u16=True: xSad8x8SearchU16 (16-bit cost surface)"""
     cur = _np(cur, np.uint8); ref_padded = _np(ref_padded, np.uint8)
     h, w = cur.shape
     assert ref_padded.shape == (h + 2 * rng, w + 2 * rng)
@@ -330,15 +338,32 @@ def xSad8x8Search(cur, ref_padded, rng, blk0=0, blk1=None, want_cost=True, want_
         blk1 = (w // 8) * (h // 8)
     side = 2 * rng + 1
     nb = blk1 - blk0
-    cost = np.empty((nb, side, side), np.uint32) if want_cost else None
+    cost = np.empty((nb, side, side), np.uint16 if u16 else np.uint32) if want_cost else None
     best = np.empty((nb, 3), np.int32) if want_best else None
-    _ck(lib().xSad8x8Search(cur.ctypes.data, ref_padded.ctypes.data, ref_padded.shape[1], w, h, rng, blk0, blk1,
-                            cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None), "xSad8x8Search")
+    fn = lib().xSad8x8SearchU16 if u16 else lib().xSad8x8Search
+    _ck(fn(cur.ctypes.data, ref_padded.ctypes.data, ref_padded.shape[1], w, h, rng, blk0, blk1,
+           cost.ctypes.data if want_cost else None, best.ctypes.data if want_best else None), "xSad8x8SearchU16" if u16 else "xSad8x8Search")
     return cost, best
 
 
 def xSad8x8SearchDev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream=0):
     _ck(lib().xSad8x8SearchDev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream), "xSad8x8SearchDev")
+
+
+def xSad8x8SearchU16Dev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSad8x8SearchU16Dev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream), "xSad8x8SearchU16Dev")
+
+
+def xSatd8x8SearchU16Dev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSatd8x8SearchU16Dev(d_cur, d_ref, strd, w, h, rng, blk0, blk1, d_cost, d_best, stream), "xSatd8x8SearchU16Dev")
+
+
+def xSatd8x8SearchTiledU16Dev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSatd8x8SearchTiledU16Dev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream), "xSatd8x8SearchTiledU16Dev")
+
+
+def xSad8x8SearchTiledU16Dev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream=0):
+    _ck(lib().xSad8x8SearchTiledU16Dev(d_cur_tiles, d_ref_tiles, width, height, rng, blk0, blk1, d_cost, d_best, stream), "xSad8x8SearchTiledU16Dev")
 
 
 def xIntra32Pred(refs, modes):

@@ -528,6 +528,7 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 5) { set_decide_v1(value); return 0; }
     if (key == 6) { set_search_acc_form(value); return 0; }
     if (key == 7) { set_sad_search_v1(value); return 0; }
+    if (key == 17) { set_search_variant(value); return 0; }
     if (key == 8) { set_intra_swar(value); return 0; }
     if (key == 9) { set_intra_ctas(value); return 0; }
     if (key == 10) { set_dct8_ctas(value); return 0; }
@@ -683,10 +684,13 @@ extern "C" int xSatd8x8Batch(const int16_t* diff, int32_t* satd, size_t n)
                        });
 }
 
-typedef cudaError_t (*search_launch_t)(const uint8_t*, const uint8_t*, intptr_t, int, int, int, size_t, size_t, uint32_t*, int32_t*, cudaStream_t);
+// CT = element type of the cost surface: uint32_t (the SURVEY 8(d) config-3 layout) or uint16_t (the ...U16 entry points)
+template <typename CT>
+using search_launch_t = cudaError_t (*)(const uint8_t*, const uint8_t*, intptr_t, int, int, int, size_t, size_t, CT*, int32_t*, cudaStream_t);
 
-static int search_dev(const char* api, search_launch_t launch, const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h,
-                      int range, size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
+template <typename CT>
+static int search_dev(const char* api, search_launch_t<CT> launch, const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h,
+                      int range, size_t blk0, size_t blk1, CT* dCost, int32_t* dBest, void* stream)
 {
     if (!dCur || !dRefPadded || w <= 0 || h <= 0 || (w & 7) || (h & 7) || range < 0 || strd < w + 2 * range || blk1 < blk0 ||
         blk1 > (size_t)(w / 8) * (h / 8))
@@ -700,8 +704,9 @@ static int search_dev(const char* api, search_launch_t launch, const uint8_t* dC
 
 // Host form of both searches: the two planes go up once (call-wide inputs), then the block range runs through the
 // chunked pipeline with no per-chunk input and up to two outputs (cost surface, argmin triples).
-static int search_host(const char* api, search_launch_t launch, const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h,
-                       int range, size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
+template <typename CT>
+static int search_host(const char* api, search_launch_t<CT> launch, const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h,
+                       int range, size_t blk0, size_t blk1, CT* cost, int32_t* best)
 {
     if (!cur || !refPadded || w <= 0 || h <= 0 || (w & 7) || (h & 7) || range < 0 || strd < w + 2 * range || blk1 < blk0 ||
         blk1 > (size_t)(w / 8) * (h / 8))
@@ -720,14 +725,14 @@ static int search_host(const char* api, search_launch_t launch, const uint8_t* c
     CK(cudaMemcpyAsync(dRef, refPadded, refBytes, cudaMemcpyHostToDevice, p.st[0]));
     CK(cudaStreamSynchronize(p.st[0]));
     const size_t side = (size_t)(2 * range + 1);
-    const size_t costUnit = side * side * 4;
+    const size_t costUnit = side * side * sizeof(CT);
     // blocks per chunk: keep a chunk's cost surface around 64 MiB
     size_t per = cost ? ((size_t)64 << 20) / costUnit : (size_t)1 << 20;
     if (per < 1) per = 1;
     const HostArr outs[2] = { { cost, costUnit }, { best, 12 } };
     if (run_chunked_on(p, nullptr, 0, outs, 2, blk1 - blk0, per,
                        [&](void* const*, void* const* dO, size_t u0, size_t nu, cudaStream_t st) {
-                           return launch(dCur, dRef, strd, w, h, range, blk0 + u0, blk0 + u0 + nu, (uint32_t*)dO[0], (int32_t*)dO[1], st);
+                           return launch(dCur, dRef, strd, w, h, range, blk0 + u0, blk0 + u0 + nu, (CT*)dO[0], (int32_t*)dO[1], st);
                        })) {
         const std::string inner(t_err);
         snprintf(t_err, sizeof(t_err), "%s: %s", api, inner.c_str());
@@ -739,25 +744,51 @@ static int search_host(const char* api, search_launch_t launch, const uint8_t* c
 extern "C" int xSatd8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
                                  size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
 {
-    return search_dev("xSatd8x8SearchDev", launch_satd8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
+    return search_dev<uint32_t>("xSatd8x8SearchDev", launch_satd8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
 }
 
 extern "C" int xSatd8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
                               size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
 {
-    return search_host("xSatd8x8Search", launch_satd8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
+    return search_host<uint32_t>("xSatd8x8Search", launch_satd8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
 }
 
 extern "C" int xSad8x8Search(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
                              size_t blk0, size_t blk1, uint32_t* cost, int32_t* best)
 {
-    return search_host("xSad8x8Search", launch_sad8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
+    return search_host<uint32_t>("xSad8x8Search", launch_sad8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
 }
 
 extern "C" int xSad8x8SearchDev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
                                 size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, void* stream)
 {
-    return search_dev("xSad8x8SearchDev", launch_sad8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
+    return search_dev<uint32_t>("xSad8x8SearchDev", launch_sad8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
+}
+
+// 16-bit cost surfaces: the same searches writing uint16_t costs (exact: an 8x8 SATD of 8-bit pixels is <= 32640, a SAD <= 16320) --
+// half the bytes of the u32 surface that dominates the searches' HBM traffic (547.6 -> 273.8 MB per 1080p +-32 frame).
+extern "C" int xSatd8x8SearchU16Dev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                                    size_t blk0, size_t blk1, uint16_t* dCost, int32_t* dBest, void* stream)
+{
+    return search_dev<uint16_t>("xSatd8x8SearchU16Dev", launch_satd8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
+}
+
+extern "C" int xSatd8x8SearchU16(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                                 size_t blk0, size_t blk1, uint16_t* cost, int32_t* best)
+{
+    return search_host<uint16_t>("xSatd8x8SearchU16", launch_satd8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
+}
+
+extern "C" int xSad8x8SearchU16Dev(const uint8_t* dCur, const uint8_t* dRefPadded, intptr_t strd, int w, int h, int range,
+                                   size_t blk0, size_t blk1, uint16_t* dCost, int32_t* dBest, void* stream)
+{
+    return search_dev<uint16_t>("xSad8x8SearchU16Dev", launch_sad8x8_search, dCur, dRefPadded, strd, w, h, range, blk0, blk1, dCost, dBest, stream);
+}
+
+extern "C" int xSad8x8SearchU16(const uint8_t* cur, const uint8_t* refPadded, intptr_t strd, int w, int h, int range,
+                                size_t blk0, size_t blk1, uint16_t* cost, int32_t* best)
+{
+    return search_host<uint16_t>("xSad8x8SearchU16", launch_sad8x8_search, cur, refPadded, strd, w, h, range, blk0, blk1, cost, best);
 }
 
 extern "C" int sad(unsigned char* input_data1, unsigned char* input_data2, size_t n)
@@ -1033,8 +1064,9 @@ extern "C" void xConvOutput420(const ref_block_t* pBlock, uint8_t* outY, const i
 
 // Full search on the encoder's own frame stores: current and reference are ref_block_t frames (m_frames[0] and m_frames[1..2],
 // src/x266.cpp:99), the reference is edge-replicated by `range` pixels here instead of by the caller.
-static int search_tiled_dev(const char* api, search_launch_t launch, const void* dCurTiles, const void* dRefTiles, int w, int h, int range,
-                            size_t blk0, size_t blk1, uint32_t* dCost, int32_t* dBest, cudaStream_t st)
+template <typename CT>
+static int search_tiled_dev(const char* api, search_launch_t<CT> launch, const void* dCurTiles, const void* dRefTiles, int w, int h, int range,
+                            size_t blk0, size_t blk1, CT* dCost, int32_t* dBest, cudaStream_t st)
 {
     if (!dCurTiles || !dRefTiles || w <= 0 || h <= 0 || (w & 15) || (h & 15) || range < 0 || blk1 < blk0 || blk1 > (size_t)(w / 8) * (h / 8))
         return fail(api, cudaSuccess);
@@ -1057,15 +1089,29 @@ static int search_tiled_dev(const char* api, search_launch_t launch, const void*
 extern "C" int xSatd8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
                                       uint32_t* dCost, int32_t* dBest, void* stream)
 {
-    return search_tiled_dev("xSatd8x8SearchTiledDev", launch_satd8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost, dBest,
+    return search_tiled_dev<uint32_t>("xSatd8x8SearchTiledDev", launch_satd8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost, dBest,
                             (cudaStream_t)stream);
 }
 
 extern "C" int xSad8x8SearchTiledDev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
                                      uint32_t* dCost, int32_t* dBest, void* stream)
 {
-    return search_tiled_dev("xSad8x8SearchTiledDev", launch_sad8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost, dBest,
+    return search_tiled_dev<uint32_t>("xSad8x8SearchTiledDev", launch_sad8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost, dBest,
                             (cudaStream_t)stream);
+}
+
+extern "C" int xSatd8x8SearchTiledU16Dev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                                         uint16_t* dCost, int32_t* dBest, void* stream)
+{
+    return search_tiled_dev<uint16_t>("xSatd8x8SearchTiledU16Dev", launch_satd8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost,
+                                      dBest, (cudaStream_t)stream);
+}
+
+extern "C" int xSad8x8SearchTiledU16Dev(const void* dCurTiles, const void* dRefTiles, int width, int height, int range, size_t blk0, size_t blk1,
+                                        uint16_t* dCost, int32_t* dBest, void* stream)
+{
+    return search_tiled_dev<uint16_t>("xSad8x8SearchTiledU16Dev", launch_sad8x8_search, dCurTiles, dRefTiles, width, height, range, blk0, blk1, dCost,
+                                      dBest, (cudaStream_t)stream);
 }
 
 // host form: the two frames go up once, the block range runs through the chunked pipeline like xSatd8x8Search

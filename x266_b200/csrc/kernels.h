@@ -44,12 +44,20 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
                                   size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
 cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                      size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st);
+// the same searches with a 16-bit cost surface (exact: SATD <= 32640, SAD <= 16320 for 8-bit pixels)
+cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                  size_t blk0, size_t blk1, uint16_t* cost, int32_t* best, cudaStream_t st);
+cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                     size_t blk0, size_t blk1, uint16_t* cost, int32_t* best, cudaStream_t st);
+cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                 size_t blk0, size_t blk1, uint16_t* cost, int32_t* best, cudaStream_t st);
 void intra_mma_table_copy(uint32_t* out);   // 35 x 256 words: the per-mode MMA fragment table of the intra kernel (host copy)
 void set_dct8_ctas(int v);        // tuning/diagnostic: CTAs per SM of the dct8 / dct4 persistent grids
 void set_dct4_ctas(int v);
 void set_intra_ctas(int v);       // tuning/diagnostic: CTAs per SM of the intra kernel's persistent grid
 void set_intra_swar(int on);      // tuning/diagnostic: CUDA-core SWAR interpolation instead of the tensor-core angular path
 void set_sad_search_v1(int on);   // tuning/diagnostic: first-generation SAD search (one CTA per block)
+void set_search_variant(int v);   // tuning/diagnostic: loop structure of the v3 search (satd_search3.cu VAR)
 void set_search_acc_form(int f);  // tuning/diagnostic: accumulate form of the v3 search (satd_packed.h maxsum4)
 cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st);
 cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, unsigned* out, cudaStream_t st);

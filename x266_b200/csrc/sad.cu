@@ -6,6 +6,16 @@
 
 namespace x266 {
 
+// acc + sum of the four byte |a-b|: ONE VABSDIFF4.U8.ACC.  Written as PTX because `__vsadu4(a, b) + acc` reaches ptxas as an
+// un-accumulated VABSDIFF4 plus a separate add, which it then gathers into 3-input IADD3s: +8 integer-ALU instructions per candidate
+// on the pipe that bounds the search (SASS of the round-2 kernel: 288 VABSDIFF4 + 128 IADD3 per vertical offset; now 288 + 2).
+__device__ __forceinline__ unsigned sad4_acc(uint32_t a, uint32_t b, unsigned acc)
+{
+    unsigned d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
+
 // ---- sad(a, b, n): one n*n-byte region pair -> one int --------------------------------------------------
 __global__ void __launch_bounds__(256)
 sad_region_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t bytes, unsigned* __restrict__ out)
@@ -27,9 +37,10 @@ sad_region_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, 
 //      words; thread <-> candidate (flattened my,mx); rows are re-aligned with funnel shifts. ------------
 constexpr int SADS_THREADS = 256;
 
+template <typename CT>
 __global__ void __launch_bounds__(SADS_THREADS)
 sad8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w, int range,
-                     size_t blk0, uint32_t* __restrict__ cost, int32_t* __restrict__ best)
+                     size_t blk0, CT* __restrict__ cost, int32_t* __restrict__ best)
 {
     extern __shared__ __align__(16) uint32_t swin[];           // [ws][wsw + 1] words
     __shared__ unsigned long long sBest[SADS_THREADS / 32];
@@ -55,7 +66,7 @@ sad8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict_
     __syncthreads();
 
     unsigned long long bestKey = ~0ull;
-    uint32_t* costBlk = cost ? cost + (size_t)blockIdx.x * side * side : nullptr;
+    CT* costBlk = cost ? cost + (size_t)blockIdx.x * side * side : nullptr;
     for (int cand = tid; cand < side * side; cand += SADS_THREADS) {
         const int my = cand / side, mx = cand - my * side;
         const int w0 = mx >> 2, sh = (mx & 3) * 8;
@@ -68,7 +79,7 @@ sad8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict_
             sb = __vsadu4(__funnelshift_r(x1, x2, sh), c[2 * r + 1]) + sb;
         }
         const unsigned s = sa + sb;
-        if (costBlk) costBlk[cand] = s;
+        if (costBlk) costBlk[cand] = (CT)s;
         const int dx = mx - range, dy = my - range;
         const unsigned long long key = ((unsigned long long)s << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
                                        ((unsigned long long)my << 12) | (unsigned long long)mx;
@@ -105,10 +116,10 @@ constexpr int SAD2_TILE = SRCH_TILE;
 constexpr int SAD2_WW = 18;                  // window pitch in words (72 bytes)
 constexpr int SAD2_CS = 20;                  // words per current block in smem: 16 + 4 pad (four blocks of a warp on distinct banks)
 
-template <int R>
+template <int R, typename CT>
 __global__ void __launch_bounds__(32, 16)
 sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w, int by0,
-                        size_t blk0, size_t blk1, uint32_t* __restrict__ cost, unsigned long long* __restrict__ keys)
+                        size_t blk0, size_t blk1, CT* __restrict__ cost, unsigned long long* __restrict__ keys)
 {
     constexpr int SIDE = 2 * R + 1;
     constexpr int NSLOT = R / 4 + 2;
@@ -192,7 +203,7 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
         }
         const int dy = my - R;
         const unsigned rank = srch_rank(dy);
-        uint32_t* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
+        CT* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) {
             if ((slotMask >> s) & 1u) {
@@ -204,22 +215,22 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
                 for (int k = 0; k < 4; k++) {
                     const uint4 c = cp[k];
                     if (s <= R / 4) {
-                        a0 = __vsadu4(A[4 * k], c.x) + a0; a1 = __vsadu4(A[4 * k + 1], c.y) + a1;
-                        a0 = __vsadu4(A[4 * k + 2], c.z) + a0; a1 = __vsadu4(A[4 * k + 3], c.w) + a1;
+                        a0 = sad4_acc(A[4 * k], c.x, a0); a1 = sad4_acc(A[4 * k + 1], c.y, a1);
+                        a0 = sad4_acc(A[4 * k + 2], c.z, a0); a1 = sad4_acc(A[4 * k + 3], c.w, a1);
                     }
                     if (s >= 1) {
-                        b0 = __vsadu4(B[4 * k], c.x) + b0; b1 = __vsadu4(B[4 * k + 1], c.y) + b1;
-                        b0 = __vsadu4(B[4 * k + 2], c.z) + b0; b1 = __vsadu4(B[4 * k + 3], c.w) + b1;
+                        b0 = sad4_acc(B[4 * k], c.x, b0); b1 = sad4_acc(B[4 * k + 1], c.y, b1);
+                        b0 = sad4_acc(B[4 * k + 2], c.z, b0); b1 = sad4_acc(B[4 * k + 3], c.w, b1);
                     }
                 }
                 if (doA) {
                     const unsigned v = a0 + a1;
-                    if (cost) cbase[s * (SIDE * SIDE - 8)] = v;
+                    if (cost) cbase[s * (SIDE * SIDE - 8)] = (CT)v;
                     keyA[s] = min(v * 128u + rank, keyA[s]);          // key as a multiply-add (FMA pipe); the ALU pipe is this kernel's limiter
                 }
                 if (doB) {
                     const unsigned v = b0 + b1;
-                    if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = v;
+                    if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = (CT)v;
                     keyB[s] = min(v * 128u + rank, keyB[s]);
                 }
             }
@@ -229,12 +240,12 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
     if (keys) srch_flush_keys<R, NSLOT>(keyA, keyB, e, (ptrdiff_t)bRow + iq - (ptrdiff_t)blk0, keys);
 }
 
-template <int R>
+template <int R, typename CT>
 static cudaError_t launch_sad_v2(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
-                                 uint32_t* cost, int32_t* best, cudaStream_t st)
+                                 CT* cost, int32_t* best, cudaStream_t st)
 {
     struct Tag {};
-    return srch_launch<R>(sad8x8_search_v2_kernel<R>, srch_attr_flag<Tag>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    return srch_launch<R>(sad8x8_search_v2_kernel<R, CT>, srch_attr_flag<Tag>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
 }
 
 static std::atomic<int> g_sadSearchV1{0};
@@ -251,8 +262,9 @@ cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
-                                 size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
+template <typename CT>
+static cudaError_t launch_sad8x8_search_as(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                           size_t blk0, size_t blk1, CT* cost, int32_t* best, cudaStream_t st)
 {
     if (blk1 <= blk0) return cudaSuccess;
     if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
@@ -265,12 +277,24 @@ cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intp
     const size_t smem = (size_t)ws * wsw * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sad8x8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sad8x8_search_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    sad8x8_search_kernel<<<(unsigned)(blk1 - blk0), SADS_THREADS, smem, st>>>(cur, refPad, strd, w, range, blk0, cost, best);
+    sad8x8_search_kernel<CT><<<(unsigned)(blk1 - blk0), SADS_THREADS, smem, st>>>(cur, refPad, strd, w, range, blk0, cost, best);
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                 size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
+{
+    return launch_sad8x8_search_as(cur, refPad, strd, w, h, range, blk0, blk1, cost, best, st);
+}
+
+cudaError_t launch_sad8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                 size_t blk0, size_t blk1, uint16_t* cost, int32_t* best, cudaStream_t st)
+{
+    return launch_sad8x8_search_as(cur, refPad, strd, w, h, range, blk0, blk1, cost, best, st);
 }
 
 } // namespace x266

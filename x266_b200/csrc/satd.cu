@@ -138,9 +138,10 @@ constexpr int SATDI_WARPS = 8;
 // ------------------------------------------------------------------------------------------------
 constexpr int SRCH_WARPS = 8;
 
+template <typename CT>
 __global__ void __launch_bounds__(SRCH_WARPS * 32)
 satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd,
-                      int w, int range, size_t blk0, uint32_t* __restrict__ cost, int32_t* __restrict__ best)
+                      int w, int range, size_t blk0, CT* __restrict__ cost, int32_t* __restrict__ best)
 {
     extern __shared__ __align__(16) uint8_t dynsm[];
     const int side = 2 * range + 1;
@@ -190,7 +191,7 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
 
     int* V = vAll + warp * 8 * wsp;
     unsigned long long bestKey = ~0ull;
-    uint32_t* costBlk = cost ? cost + (size_t)blockIdx.x * side * side : nullptr;
+    CT* costBlk = cost ? cost + (size_t)blockIdx.x * side * side : nullptr;
 
     for (int my = warp; my < side; my += SRCH_WARPS) {
         // vertical transforms of the 8-row band starting at window row my
@@ -218,7 +219,7 @@ satd8x8_search_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
                 }
             }
             const unsigned c4 = (sa + sb + 2) >> 2;
-            if (costBlk) costBlk[my * side + mx] = c4;
+            if (costBlk) costBlk[my * side + mx] = (CT)c4;
             const int dx = mx - range, dy = my - range;
             const unsigned long long key = ((unsigned long long)c4 << 40) | ((unsigned long long)(dx * dx + dy * dy) << 24) |
                                            ((unsigned long long)my << 12) | (unsigned long long)mx;
@@ -415,8 +416,9 @@ cudaError_t launch_satd8x8_batch(const int16_t* diff, int32_t* out, size_t n, cu
     return cudaGetLastError();
 }
 
-cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
-                                  size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
+template <typename CT>
+static cudaError_t launch_satd8x8_search_as(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                            size_t blk0, size_t blk1, CT* cost, int32_t* best, cudaStream_t st)
 {
     if (blk1 <= blk0) return cudaSuccess;
     if (range < 0 || range > 2047 || (w & 7) || (h & 7) || blk1 > (size_t)(w / 8) * (h / 8)) return cudaErrorInvalidValue;
@@ -426,14 +428,28 @@ cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, int
     const size_t smem = 128 * sizeof(int) + (size_t)SRCH_WARPS * 8 * wsp * sizeof(int) + (size_t)ws * wsp;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(satd8x8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(satd8x8_search_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const size_t nb = blk1 - blk0;
     // grid.x is limited to 2^31-1; frames are far below that
-    satd8x8_search_kernel<<<(unsigned)nb, SRCH_WARPS * 32, smem, st>>>(cur, refPad, strd, w, range, blk0, cost, best);
+    satd8x8_search_kernel<CT><<<(unsigned)nb, SRCH_WARPS * 32, smem, st>>>(cur, refPad, strd, w, range, blk0, cost, best);
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                  size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
+{
+    return launch_satd8x8_search_as(cur, refPad, strd, w, h, range, blk0, blk1, cost, best, st);
+}
+
+// 16-bit cost surface: exact, because an 8x8 SATD of 8-bit pixels cannot exceed 32640 (sum_k |T_k| <= sqrt(64) ||T||_2 = 8 * 8 ||x||_2
+// <= 64 * 8 * 255 = 130560 before the >> 2 of satd.c:113) and an 8x8 SAD cannot exceed 16320
+cudaError_t launch_satd8x8_search(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                  size_t blk0, size_t blk1, uint16_t* cost, int32_t* best, cudaStream_t st)
+{
+    return launch_satd8x8_search_as(cur, refPad, strd, w, h, range, blk0, blk1, cost, best, st);
 }
 
 } // namespace x266

@@ -28,6 +28,7 @@
 // candidate are the floor; the sums therefore go to the FMA pipe (one IDP.2A per word, satd_packed.h maxsum4<1>).
 #include "search_tile.cuh"
 #include "satd_packed.h"
+#include <type_traits>
 
 namespace x266 {
 
@@ -36,10 +37,18 @@ constexpr int S3_WP = 72;                    // window pitch in bytes: 64 positi
 constexpr int S3_TCS = 36;                   // T(cur) row: 32 words + 64*cur[0][0] + pad (16-byte rows, distinct banks for 4 blocks)
 constexpr int S3_CTAS_PER_SM = 16;
 
-template <int R, int ACCF, int NCH>
-__global__ void __launch_bounds__(32, S3_CTAS_PER_SM)
+// VAR 0: every slot unrolled, running keys in registers (the round-1/2 body).
+// VAR 1: slots 2..R/4 (both positions live in all lanes) as ONE rolled loop body with the running keys in shared memory (per-lane words,
+//        shared-memory atomic min = LSU pipe) -- the unrolled body is 27 KB of SASS for 16 warps that sit in 16 different places of it
+//        (ncu: 8 % of the stall samples are no_inst); the three edge slots stay peeled.  The candidate's constant terms ride in the
+//        accumulator's initial value: acc0 = -(64 ref00 + 2 BIAS - 2)/2 - 32 cur00, cost = acc >> 1.
+// VAR 2: VAR 1 + the two candidates per group that only lane e == 0 owns (mx = 2R: slot 0 of position A, slot 1 of position B) are
+//        computed by the 8 lanes of the group together, 4 words each, instead of by full 32-word passes with 7 of 8 lanes discarded.
+// VAR 3 / 4: VAR 1 compiled for 20 / 22 resident warps per SM (96 / 88 registers: the rolled body no longer holds the 20 key registers).
+template <int R, int ACCF, int NCH, typename CT, int VAR>
+__global__ void __launch_bounds__(32, VAR == 3 ? 20 : VAR == 4 ? 22 : S3_CTAS_PER_SM)
 satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refPad, intptr_t strd, int w, int by0,
-                         size_t blk0, size_t blk1, uint32_t* __restrict__ cost, unsigned long long* __restrict__ keys)
+                         size_t blk0, size_t blk1, CT* __restrict__ cost, unsigned long long* __restrict__ keys)
 {
     constexpr int SIDE = 2 * R + 1;
     constexpr int WS = 2 * R + 8;
@@ -52,6 +61,8 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     __shared__ __align__(16) uint8_t curw[8][128];
     __shared__ __align__(16) uint32_t V[S3_WP][4];
     __shared__ __align__(16) uint32_t tcur[NBLK][S3_TCS];
+    __shared__ unsigned skey[VAR ? 2 * NSLOT : 1][32];           // VAR >= 1: running keys, [slot][lane] (A) and [NSLOT + slot][lane] (B)
+    __shared__ __align__(16) uint32_t sedge[VAR == 2 ? 4 : 1][2][36];   // VAR 2: T(ref) of positions A and B of the lanes e == 0
 
     const int lane = threadIdx.x;
     const int g = lane >> 3, e = lane & 7;
@@ -74,6 +85,10 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     unsigned keyA[NSLOT], keyB[NSLOT];           // per (slot, position): cost << 7 | rank(my); mx is fixed per entry
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) keyA[s] = keyB[s] = 0xFFFFFFFFu;
+    if (VAR) {
+#pragma unroll
+        for (int s = 0; s < 2 * NSLOT; s++) skey[s][lane] = 0xFFFFFFFFu;
+    }
 
     // ---- stage the window rows of this chunk, the current blocks and T(cur)
     {
@@ -128,7 +143,7 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
                 uint32_t* d = tcur[k8 * 8 + lane];
 #pragma unroll
                 for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(d + 4 * k) = make_uint4(T[4 * k], T[4 * k + 1], T[4 * k + 2], T[4 * k + 3]);
-                d[32] = 64u * curw[0][64 * k8 + 8 * lane];
+                d[32] = VAR ? 0u - 32u * curw[0][64 * k8 + 8 * lane] : 64u * curw[0][64 * k8 + 8 * lane];
             }
             __syncwarp();
         }
@@ -171,36 +186,117 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
         const int dy = my - R;
         const unsigned rank = srch_rank(dy);
         // cost index of (slot s, position A) = cbase + s * (SIDE*SIDE - 8); position B: + 8
-        uint32_t* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
+        CT* cbase = cost ? cost + (((ptrdiff_t)bRow + iq - (ptrdiff_t)blk0) * SIDE + my) * SIDE + e + 2 * R : nullptr;
 
-#pragma unroll
-        for (int s = 0; s < NSLOT; s++) {
-            if ((slotMask >> s) & 1u) {
-                const bool doA = (s <= R / 4) && (s >= 1 || e == 0);
-                const bool doB = (s >= 1) && (s >= 2 || e == 0);
+        if (VAR == 0) {
+    #pragma unroll
+            for (int s = 0; s < NSLOT; s++) {
+                if ((slotMask >> s) & 1u) {
+                    const bool doA = (s <= R / 4) && (s >= 1 || e == 0);
+                    const bool doB = (s >= 1) && (s >= 2 || e == 0);
+                    const uint32_t* tc = tcur[2 * g + s];
+                    uint32_t accA = 0, accB = 0;
+    #pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint4 c = *reinterpret_cast<const uint4*>(tc + 4 * k);
+                        if (s <= R / 4) accA = s3::maxsum4<ACCF>(&TA[4 * k], c.x, c.y, c.z, c.w, accA);
+                        if (s >= 1) accB = s3::maxsum4<ACCF>(&TB[4 * k], c.x, c.y, c.z, c.w, accB);
+                    }
+                    const uint32_t c64 = tc[32];
+                    // the tail of a candidate on the FMA pipe: x >> 2 as the high word of x * 2^30, key = cost * 128 + rank as a multiply-add;
+                    // only the running minimum needs the integer ALU pipe (the limiter of this kernel)
+                    if (doA) {
+                        const uint32_t c4 = __umulhi(2u * accA - subA - c64, 1u << 30);
+                        if (cost) cbase[s * (SIDE * SIDE - 8)] = (CT)c4;
+                        keyA[s] = min(c4 * 128u + rank, keyA[s]);
+                    }
+                    if (doB) {
+                        const uint32_t c4 = __umulhi(2u * accB - subB - c64, 1u << 30);
+                        if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = (CT)c4;
+                        keyB[s] = min(c4 * 128u + rank, keyB[s]);
+                    }
+                }
+            }
+        } else {
+            // constant terms of a candidate in the accumulator's initial value (tcur[.][32] = -32 cur00): cost = acc >> 1
+            const uint32_t hA = 0u - (32u * wrow[xa] + (uint32_t)s3::BIAS_SUM - 1u);
+            const uint32_t hB = 0u - (32u * wrow[xa + 8] + (uint32_t)s3::BIAS_SUM - 1u);
+            const uint32_t keyRank = rank;
+            // one (slot, position pair): DOA / DOB = which positions every lane of the warp computes
+            auto slot = [&](int s, auto doAc, auto doBc, bool wrA, bool wrB) {
+                constexpr bool DOA = decltype(doAc)::value, DOB = decltype(doBc)::value;
                 const uint32_t* tc = tcur[2 * g + s];
-                uint32_t accA = 0, accB = 0;
+                const uint32_t c32 = tc[32];
+                uint32_t accA = hA + c32, accB = hB + c32;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const uint4 c = *reinterpret_cast<const uint4*>(tc + 4 * k);
-                    if (s <= R / 4) accA = s3::maxsum4<ACCF>(&TA[4 * k], c.x, c.y, c.z, c.w, accA);
-                    if (s >= 1) accB = s3::maxsum4<ACCF>(&TB[4 * k], c.x, c.y, c.z, c.w, accB);
+                    if (DOA) accA = s3::maxsum4<ACCF>(&TA[4 * k], c.x, c.y, c.z, c.w, accA);
+                    if (DOB) accB = s3::maxsum4<ACCF>(&TB[4 * k], c.x, c.y, c.z, c.w, accB);
                 }
-                const uint32_t c64 = tc[32];
-                // the tail of a candidate on the FMA pipe: x >> 2 as the high word of x * 2^30, key = cost * 128 + rank as a multiply-add;
-                // only the running minimum needs the integer ALU pipe (the limiter of this kernel)
-                if (doA) {
-                    const uint32_t c4 = __umulhi(2u * accA - subA - c64, 1u << 30);
-                    if (cost) cbase[s * (SIDE * SIDE - 8)] = c4;
-                    keyA[s] = min(c4 * 128u + rank, keyA[s]);
+                if (DOA && wrA) {
+                    const uint32_t c4 = __umulhi(accA, 1u << 31);
+                    if (cost) cbase[s * (SIDE * SIDE - 8)] = (CT)c4;
+                    atomicMin(&skey[s][lane], c4 * 128u + keyRank);
                 }
-                if (doB) {
-                    const uint32_t c4 = __umulhi(2u * accB - subB - c64, 1u << 30);
-                    if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = c4;
-                    keyB[s] = min(c4 * 128u + rank, keyB[s]);
+                if (DOB && wrB) {
+                    const uint32_t c4 = __umulhi(accB, 1u << 31);
+                    if (cost) cbase[s * (SIDE * SIDE - 8) + 8] = (CT)c4;
+                    atomicMin(&skey[NSLOT + s][lane], c4 * 128u + keyRank);
                 }
+            };
+            using T_ = std::true_type;
+            using F_ = std::false_type;
+            if (VAR == 2) {
+                // the candidates mx = 2R: (position A of lane (g,0), block 2g) and (position B of lane (g,0), block 2g+1), 4 words per lane
+                if (e == 0) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        *reinterpret_cast<uint4*>(&sedge[g][0][4 * k]) = make_uint4(TA[4 * k], TA[4 * k + 1], TA[4 * k + 2], TA[4 * k + 3]);
+                        *reinterpret_cast<uint4*>(&sedge[g][1][4 * k]) = make_uint4(TB[4 * k], TB[4 * k + 1], TB[4 * k + 2], TB[4 * k + 3]);
+                    }
+                }
+                __syncwarp();
+                const uint4 ta = *reinterpret_cast<const uint4*>(&sedge[g][0][4 * e]);
+                const uint4 tb = *reinterpret_cast<const uint4*>(&sedge[g][1][4 * e]);
+                const uint4 ca = *reinterpret_cast<const uint4*>(&tcur[2 * g][4 * e]);
+                const uint4 cb = *reinterpret_cast<const uint4*>(&tcur[2 * g + 1][4 * e]);
+                const uint32_t tav[4] = { ta.x, ta.y, ta.z, ta.w }, tbv[4] = { tb.x, tb.y, tb.z, tb.w };
+                uint32_t pa = s3::maxsum4<ACCF>(tav, ca.x, ca.y, ca.z, ca.w, 0u);
+                uint32_t pb = s3::maxsum4<ACCF>(tbv, cb.x, cb.y, cb.z, cb.w, 0u);
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                    pb += __shfl_xor_sync(0xffffffffu, pb, o);
+                }
+                __syncwarp();                        // sedge may be rewritten by the next vertical offset
+                if (e == 0) {
+                    if (slotMask & 1u) {
+                        const uint32_t c4 = __umulhi(pa + hA + tcur[2 * g][32], 1u << 31);
+                        if (cost) cbase[0] = (CT)c4;
+                        atomicMin(&skey[0][lane], c4 * 128u + keyRank);
+                    }
+                    if (slotMask & 2u) {
+                        const uint32_t c4 = __umulhi(pb + hB + tcur[2 * g + 1][32], 1u << 31);
+                        if (cost) cbase[(SIDE * SIDE - 8) + 8] = (CT)c4;
+                        atomicMin(&skey[NSLOT + 1][lane], c4 * 128u + keyRank);
+                    }
+                }
+                if (slotMask & 2u) slot(1, T_{}, F_{}, true, false);
+            } else {
+                if (slotMask & 1u) slot(0, T_{}, F_{}, e == 0, false);
+                if (slotMask & 2u) slot(1, T_{}, T_{}, true, e == 0);
             }
+#pragma unroll 1
+            for (int s = 2; s <= R / 4; s++)
+                if ((slotMask >> s) & 1u) slot(s, T_{}, T_{}, true, true);
+            if ((slotMask >> (R / 4 + 1)) & 1u) slot(R / 4 + 1, F_{}, T_{}, false, true);
         }
+    }
+    if (VAR) {
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) { keyA[s] = skey[s][lane]; keyB[s] = skey[NSLOT + s][lane]; }
     }
     if (keys) srch_flush_keys<R, NSLOT>(keyA, keyB, e, (ptrdiff_t)bRow + iq - (ptrdiff_t)blk0, keys);
 }
@@ -217,32 +313,62 @@ __global__ void srch_keys_decode_kernel(const unsigned long long* __restrict__ k
 
 static std::atomic<int> g_accForm{1};
 void set_search_acc_form(int f) { g_accForm = f; }
+static std::atomic<int> g_searchVar{0};
+void set_search_variant(int v) { g_searchVar = v; }
 
-template <int R, int ACCF>
+template <int R, int ACCF, typename CT>
 static cudaError_t launch_v3f(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
-                              uint32_t* cost, int32_t* best, cudaStream_t st)
+                              CT* cost, int32_t* best, cudaStream_t st)
 {
-    struct Tag {};
-    return srch_launch<R>(satd8x8_search_v3_kernel<R, ACCF, srch_chunks<R>()>, srch_attr_flag<Tag>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    struct Tag0 {};
+    struct Tag1 {};
+    struct Tag2 {};
+    struct Tag3 {};
+    struct Tag4 {};
+    if (ACCF == 1 && g_searchVar == 1)
+        return srch_launch<R>(satd8x8_search_v3_kernel<R, 1, srch_chunks<R>(), CT, 1>, srch_attr_flag<Tag1>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (ACCF == 1 && g_searchVar == 2)
+        return srch_launch<R>(satd8x8_search_v3_kernel<R, 1, srch_chunks<R>(), CT, 2>, srch_attr_flag<Tag2>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (ACCF == 1 && g_searchVar == 3)
+        return srch_launch<R>(satd8x8_search_v3_kernel<R, 1, srch_chunks<R>(), CT, 3>, srch_attr_flag<Tag3>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (ACCF == 1 && g_searchVar == 4)
+        return srch_launch<R>(satd8x8_search_v3_kernel<R, 1, srch_chunks<R>(), CT, 4>, srch_attr_flag<Tag4>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    return srch_launch<R>(satd8x8_search_v3_kernel<R, ACCF, srch_chunks<R>(), CT, 0>, srch_attr_flag<Tag0>(), cur, refPad, strd, w, blk0, blk1, cost, best, st);
 }
 
-template <int R>
+template <int R, typename CT>
 static cudaError_t launch_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
-                             uint32_t* cost, int32_t* best, cudaStream_t st)
+                             CT* cost, int32_t* best, cudaStream_t st)
 {
-    if (g_accForm == 0) return launch_v3f<R, 0>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
-    if (g_accForm == 2) return launch_v3f<R, 2>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (sizeof(CT) == 4) {                           // the alternative accumulate forms exist for the u32 surface only (diagnostic)
+        if (g_accForm == 0) return launch_v3f<R, 0>(cur, refPad, strd, w, blk0, blk1, (uint32_t*)cost, best, st);
+        if (g_accForm == 2) return launch_v3f<R, 2>(cur, refPad, strd, w, blk0, blk1, (uint32_t*)cost, best, st);
+    }
     return launch_v3f<R, 1>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+}
+
+template <typename CT>
+static cudaError_t launch_v3_any(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int range,
+                                 size_t blk0, size_t blk1, CT* cost, int32_t* best, cudaStream_t st)
+{
+    if (range == 32) return launch_v3<32>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (range == 16) return launch_v3<16>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    if (range == 8) return launch_v3<8>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
                                      size_t blk0, size_t blk1, uint32_t* cost, int32_t* best, cudaStream_t st)
 {
     (void)h;
-    if (range == 32) return launch_v3<32>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
-    if (range == 16) return launch_v3<16>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
-    if (range == 8) return launch_v3<8>(cur, refPad, strd, w, blk0, blk1, cost, best, st);
-    return cudaErrorInvalidValue;
+    return launch_v3_any(cur, refPad, strd, w, range, blk0, blk1, cost, best, st);
+}
+
+cudaError_t launch_satd8x8_search_v3(const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, int h, int range,
+                                     size_t blk0, size_t blk1, uint16_t* cost, int32_t* best, cudaStream_t st)
+{
+    (void)h;
+    return launch_v3_any(cur, refPad, strd, w, range, blk0, blk1, cost, best, st);
 }
 
 } // namespace x266

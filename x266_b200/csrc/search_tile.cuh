@@ -52,9 +52,9 @@ __global__ void srch_keys_decode_kernel(const unsigned long long* __restrict__ k
 
 // Launches `kern` (signature of both search kernels) over the units that cover blocks [blk0, blk1), with the stream-ordered key scratch
 // and the decode kernel when the argmin is wanted.
-template <int R, typename Kern>
+template <int R, typename Kern, typename CT>
 static cudaError_t srch_launch(Kern kern, std::atomic<bool>& attrSet, const uint8_t* cur, const uint8_t* refPad, intptr_t strd, int w, size_t blk0, size_t blk1,
-                               uint32_t* cost, int32_t* best, cudaStream_t st)
+                               CT* cost, int32_t* best, cudaStream_t st)
 {
     const int bw = w / 8;
     const int y0 = (int)(blk0 / bw), y1 = (int)((blk1 - 1) / bw);
