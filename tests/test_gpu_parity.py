@@ -237,16 +237,8 @@ def test_satd_search_small(x266, orc, rng_px, v1):
     assert np.array_equal(best, wb)
 
 
-@pytest.fixture(params=[0, 1, 2])
-def search_var(request, x266):
-    """loop structure of the v3 SATD search (xGpuTune 17; satd_search3.cu VAR)"""
-    x266.tune(17, request.param)
-    yield request.param
-    x266.tune(17, 0)
-
-
 @pytest.mark.parametrize("rng_px", [8, 16, 32])
-def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px, search_var):
+def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px):
     """width 200 = one full strip of 16 blocks + a ragged strip of 9; block sub-ranges that start and end
     mid-strip / mid-row; extreme flat frames (all ties -> the tie-break rule decides)."""
     cur, refp = make_frames(200, 24, rng_px, seed=5)
@@ -266,7 +258,7 @@ def test_satd_search_ragged_strips_and_subranges(x266, orc, rng_px, search_var):
 
 
 @pytest.mark.parametrize("rng_px", [8, 16, 32])
-def test_satd_search_extreme_patterns(x266, orc, rng_px, search_var):
+def test_satd_search_extreme_patterns(x266, orc, rng_px):
     """v3 keeps two biased coefficients per 32-bit word: frames built from the 64 Hadamard basis patterns (pixels
     0/255, every coefficient driven to +-8160 / 16320) and from random 0/255 pixels must not carry between halves."""
     r = np.random.default_rng(11)

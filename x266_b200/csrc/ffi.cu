@@ -528,7 +528,6 @@ extern "C" int xGpuTune(int key, int value)
     if (key == 5) { set_decide_v1(value); return 0; }
     if (key == 6) { set_search_acc_form(value); return 0; }
     if (key == 7) { set_sad_search_v1(value); return 0; }
-    if (key == 17) { set_search_variant(value); return 0; }
     if (key == 8) { set_intra_swar(value); return 0; }
     if (key == 9) { set_intra_ctas(value); return 0; }
     if (key == 10) { set_dct8_ctas(value); return 0; }

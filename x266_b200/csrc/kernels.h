@@ -57,7 +57,6 @@ void set_dct4_ctas(int v);
 void set_intra_ctas(int v);       // tuning/diagnostic: CTAs per SM of the intra kernel's persistent grid
 void set_intra_swar(int on);      // tuning/diagnostic: CUDA-core SWAR interpolation instead of the tensor-core angular path
 void set_sad_search_v1(int on);   // tuning/diagnostic: first-generation SAD search (one CTA per block)
-void set_search_variant(int v);   // tuning/diagnostic: loop structure of the v3 search (satd_search3.cu VAR)
 void set_search_acc_form(int f);  // tuning/diagnostic: accumulate form of the v3 search (satd_packed.h maxsum4)
 cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint32_t* cost, int32_t* bestMode, size_t n, cudaStream_t st);
 cudaError_t launch_sad_region(const uint8_t* a, const uint8_t* b, size_t bytes, unsigned* out, cudaStream_t st);
