@@ -56,6 +56,15 @@ __device__ __forceinline__ void cp_async16(uint32_t smemAddr, const void* g)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smemAddr), "l"(g) : "memory");
 }
+// 4- and 8-byte asynchronous copies (cp.async.ca, SASS LDGSTS); srcBytes = 0 zero-fills the destination without touching g
+__device__ __forceinline__ void cp_async4(uint32_t smemAddr, const void* g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smemAddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(uint32_t smemAddr, const void* g, int srcBytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smemAddr), "l"(g), "r"(srcBytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 

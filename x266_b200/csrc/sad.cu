@@ -150,13 +150,16 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) keyA[s] = keyB[s] = 0xFFFFFFFFu;
 
-    {   // stage the window rows of this chunk and the current blocks
+    {   // stage the window rows of this chunk and the current blocks.  Aligned planes go through asynchronous copies: a single-warp CTA
+        // has nothing to overlap its own prologue with, and with load -> STS loops every group of loads is one exposed round trip to L2 /
+        // HBM -- under the cost surface's write traffic those were 22 % of the warps' time (ncu: long_scoreboard on the prologue's STS).
         const uint8_t* wsrc = refPad + ((intptr_t)by8 * 8 + my0) * strd + P0;
         const int rows = my1 - my0 + 7;
         if ((((uintptr_t)wsrc | (uintptr_t)strd) & 3) == 0 && P0 + 4 * SAD2_WW <= padW) {
+            const uint32_t winS = (uint32_t)__cvta_generic_to_shared(win);
             for (int idx = lane; idx < rows * SAD2_WW; idx += 32) {
                 const int yy = idx / SAD2_WW, xx = idx - yy * SAD2_WW;
-                win[idx] = __ldg(reinterpret_cast<const uint32_t*>(wsrc + (intptr_t)yy * strd) + xx);
+                cp_async4(winS + 4u * idx, reinterpret_cast<const uint32_t*>(wsrc + (intptr_t)yy * strd) + xx);
             }
         } else {
             uint8_t* wb = reinterpret_cast<uint8_t*>(win);
@@ -166,12 +169,12 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
             }
         }
         if ((((uintptr_t)cur | (uintptr_t)w) & 7) == 0) {
+            const uint32_t curS = (uint32_t)__cvta_generic_to_shared(curs);
             for (int idx = lane; idx < 8 * NBLK; idx += 32) {
                 const int r = idx / NBLK, t = idx - r * NBLK;
                 const int i = iBase + t;
-                uint2 v = make_uint2(0u, 0u);
-                if (i >= 0 && i < bw) v = __ldg(reinterpret_cast<const uint2*>(cur + (size_t)(by8 * 8 + r) * w + i * 8));
-                *reinterpret_cast<uint2*>(&curs[t * SAD2_CS + 2 * r]) = v;
+                const bool in = i >= 0 && i < bw;
+                cp_async8_zfill(curS + 4u * (t * SAD2_CS + 2 * r), cur + (size_t)(by8 * 8 + r) * w + (in ? i : 0) * 8, in ? 8 : 0);
             }
         } else {
             uint8_t* cb = reinterpret_cast<uint8_t*>(curs);
@@ -181,6 +184,8 @@ sad8x8_search_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
                 cb[t * SAD2_CS * 4 + r * 8 + c] = (i >= 0 && i < bw) ? cur[(size_t)(by8 * 8 + r) * w + i * 8 + c] : (uint8_t)0;
             }
         }
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncwarp();
     }
 

@@ -85,10 +85,12 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
     {
         const uint8_t* wsrc = refPad + ((intptr_t)by8 * 8 + my0) * strd + P0;
         const int rows = my1 - my0 + 7;
+        // aligned planes: asynchronous copies, ONE exposed round trip for the whole prologue instead of one per group of loads (see sad.cu)
         if ((((uintptr_t)wsrc | (uintptr_t)strd) & 3) == 0 && P0 + S3_WP <= padW) {
+            const uint32_t winS = (uint32_t)__cvta_generic_to_shared(win);
             for (int idx = lane; idx < rows * (S3_WP / 4); idx += 32) {
                 const int yy = idx / (S3_WP / 4), xx = idx - yy * (S3_WP / 4);
-                reinterpret_cast<uint32_t*>(win)[idx] = __ldg(reinterpret_cast<const uint32_t*>(wsrc + (intptr_t)yy * strd) + xx);
+                cp_async4(winS + 4u * idx, reinterpret_cast<const uint32_t*>(wsrc + (intptr_t)yy * strd) + xx);
             }
         } else {
             for (int idx = lane; idx < rows * S3_WP; idx += 32) {
@@ -97,12 +99,12 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
             }
         }
         if ((((uintptr_t)cur | (uintptr_t)w) & 7) == 0) {        // 8 pixels of a block row per load
+            const uint32_t curS = (uint32_t)__cvta_generic_to_shared(&curw[0][0]);
             for (int idx = lane; idx < 8 * 16; idx += 32) {
                 const int r = idx >> 4, x8 = idx & 15;
                 const int i = iBase + x8;
-                uint2 v = make_uint2(0u, 0u);
-                if (x8 < NBLK && i >= 0 && i < bw) v = __ldg(reinterpret_cast<const uint2*>(cur + (size_t)(by8 * 8 + r) * w + i * 8));
-                *reinterpret_cast<uint2*>(&curw[r][8 * x8]) = v;
+                const bool in = x8 < NBLK && i >= 0 && i < bw;
+                cp_async8_zfill(curS + 128u * r + 8u * x8, cur + (size_t)(by8 * 8 + r) * w + (in ? i : 0) * 8, in ? 8 : 0);
             }
         } else {
             for (int idx = lane; idx < 8 * 128; idx += 32) {
@@ -111,6 +113,8 @@ satd8x8_search_v3_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
                 curw[r][x] = (x < NBLK * 8 && i >= 0 && i < bw) ? cur[(size_t)(by8 * 8 + r) * w + i * 8 + (x & 7)] : (uint8_t)0;
             }
         }
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncwarp();
 #pragma unroll 1
         for (int k8 = 0; k8 * 8 < NBLK; k8++) {      // blocks 8*k8 .. 8*k8+7, with the code path of the window
