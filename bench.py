@@ -397,14 +397,15 @@ class Env:
         return e
 
 
-def search_entry(env, name, ms, cands_per_gpu, config, cpu=None):
+def search_entry(env, name, ms, cands_per_gpu, config, cpu=None, surface_bytes=4):
     torch = env.torch
     props = torch.cuda.get_device_properties(env.dev)
     clk_hz = getattr(props, "clock_rate", 1965000) * 1e3
     # the bound that applies: the integer ALU pipe issues one warp instruction per two cycles per SM sub-partition;
     # a SATD candidate needs 32 VIMNMX.S16x2 on it, a SAD candidate 16 VABSDIFF4 -- nothing else counted
     alu_peak = props.multi_processor_count * 4 * clk_hz / 2 * 32 / (32 if name.startswith("satd") else 16)
-    gbs = SEARCH_BYTES_1080P / (ms * 1e-3) / 1e9
+    # algorithmic bytes of a 1080p +-32 frame: both planes + the cost surface at its element size (+ 12 B per block of argmins)
+    gbs = (SEARCH_BYTES_1080P - (4 - surface_bytes) * 136890000 + (0 if surface_bytes else 32400 * 12)) / (ms * 1e-3) / 1e9
     return {"metric": name, "value": env.world * cands_per_gpu / (ms * 1e-3), "n_gpus": env.world, "ms_per_frame": ms, "cpu_baseline": cpu,
             "alu_pipe_bound": {"peak": alu_peak, "unit": "candidates/s per GPU", "frac": cands_per_gpu / (ms * 1e-3) / alu_peak,
                                "model": "32 VIMNMX.S16x2 (SATD) / 16 VABSDIFF4 (SAD) per candidate, 1 ALU warp instruction per 2 cycles per sub-partition"},
@@ -537,6 +538,14 @@ def secondary_section(env, src, dst, n_blocks, cpu):
         ms = env.timed(lambda: fn(cur.data_ptr(), refp.data_ptr(), w + 2 * rg, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st), 5)
         secondary.append(search_entry(env, name, ms, nb * 65 * 65, "config3: 1920x1080 per GPU, +-32, u32 cost surface + argmin",
                                       satd_cpu if name.startswith("satd") else None))
+    # the same searches with the 16-bit cost surface (xS*SearchU16Dev; exact, half the surface bytes) and with the argmins only
+    for name, fn16, fn in (("satd8x8_search", xb.xSatd8x8SearchU16Dev, xb.xSatd8x8SearchDev), ("sad8x8_search", xb.xSad8x8SearchU16Dev, xb.xSad8x8SearchDev)):
+        ms = env.timed(lambda: fn16(cur.data_ptr(), refp.data_ptr(), w + 2 * rg, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st), 5)
+        secondary.append(search_entry(env, name + "_u16_surface_candidates_per_s", ms, nb * 65 * 65,
+                                      "config3 frame, +-32, u16 cost surface + argmin", surface_bytes=2))
+        ms = env.timed(lambda: fn(cur.data_ptr(), refp.data_ptr(), w + 2 * rg, w, h, rg, 0, nb, 0, best.data_ptr(), st), 5)
+        secondary.append(search_entry(env, name + "_argmin_only_candidates_per_s", ms, nb * 65 * 65,
+                                      "config3 frame, +-32, argmin triples only (no cost surface)", surface_bytes=0))
     del cur, refp, cost, best
     # config 2: one 1080p frame of residuals (2040 blocks) -- latency of a single launch
     ms = env.timed(lambda: xb.xDct32BatchDev(sp, dp, 2040, SHIFTS[0], SHIFTS[1], st), 200, warm=20)
@@ -783,6 +792,15 @@ def bench_config3(env):
 
     sec = env.wall(host_call, 3, warm=1)
     e2e_ok = bool(torch.equal(hbest, best.cpu()) and torch.equal(hcost, cost.cpu()))
+    # the same call with the 16-bit cost surface (xSatd8x8SearchU16): the D2H copy of the surface is what the end-to-end time consists of
+    hcost16 = hcost.view(torch.int16).view(-1)[:nb * 65 * 65].view(nb, 65, 65)
+
+    def host_call16():
+        rc = L.xSatd8x8SearchU16(hc.data_ptr(), hr.data_ptr(), w + 2 * rg, w, h, rg, 0, nb, hcost16.data_ptr(), hbest.data_ptr())
+        assert rc == 0, xb.last_error()
+
+    sec16 = env.wall(host_call16, 3, warm=1)
+    e2e16_ok = bool(torch.equal(hbest, best.cpu()) and torch.equal(hcost16.to(torch.int32), cost.cpu()))
     cpu = None
     env.unbind()
     if rank == 0:
@@ -806,6 +824,9 @@ def bench_config3(env):
         "e2e": {"value": world * cands / sec, "unit": "candidates/s", "h2d_bytes_per_step": world * (hc.numel() + hr.numel()),
                 "d2h_bytes_per_step": world * (hcost.numel() * 4 + hbest.numel() * 4), "api": "xSatd8x8Search (host pointers, pinned)",
                 "matches_device_path": e2e_ok},
+        "e2e_u16_surface": {"value": world * cands / sec16, "unit": "candidates/s", "h2d_bytes_per_step": world * (hc.numel() + hr.numel()),
+                            "d2h_bytes_per_step": world * (hcost16.numel() * 2 + hbest.numel() * 4),
+                            "api": "xSatd8x8SearchU16 (host pointers, pinned; 16-bit cost surface, exact)", "matches_device_path": e2e16_ok},
         "gpu_launches": t["launches"], "clocks": t["clocks"], "secondary": [],
     }
 
