@@ -168,11 +168,9 @@ __device__ __forceinline__ void intra_generate(int mode, uint8_t* __restrict__ s
             const uint32_t keep = q4 == 3 ? 0x00FFFFFFu : 0xFFFFFFFFu, one = q4 == 3 ? 0x01000000u : 0u;   // Hankel row k = 31 := 1
             if (!EARLYTAB) { T0 = __ldg(tp); T1 = __ldg(tp + 32); }
             uint8_t* orow = reinterpret_cast<uint8_t*>(out) + g4 * 32 + 8 * q4;      // row g, pixels 8q..8q+7
-            // pixel = byte 1 of each sum: four sums -> one word
-            auto word = [](const int (&a)[4], const int (&b)[4], int r) {
-                return __byte_perm(__byte_perm((uint32_t)a[2 * r], (uint32_t)a[2 * r + 1], 0x5151),
-                                   __byte_perm((uint32_t)b[2 * r], (uint32_t)b[2 * r + 1], 0x5151), 0x5410);
-            };
+            // pixel = byte 1 of each sum: four sums -> one word (merge on the FMA pipe, intra_dev.cuh)
+            const uint32_t k16 = intra_k16();
+            auto word = [k16](const int (&a)[4], const int (&b)[4], int r) { return intra_word_fma(a, b, r, k16); };
             if (isVer) {
                 // B = Hankel windows with permuted columns: column n = g of tile t is pixel 8(g>>1) + 2t + (g&1)
                 const int cb = ref0 + base + 4 * q4 + 8 * (g4 >> 1) + (g4 & 1);
@@ -298,10 +296,8 @@ __device__ __forceinline__ void intra_generate(int mode, uint8_t* __restrict__ s
             Bf[t] = q4 == 0 ? v : q4 == 1 ? 1u : 0u;
         }
         uint8_t* orow = reinterpret_cast<uint8_t*>(out) + g4 * 32 + 8 * q4;
-        auto word = [](const int (&a)[4], const int (&b)[4], int r) {
-            return __byte_perm(__byte_perm((uint32_t)a[2 * r], (uint32_t)a[2 * r + 1], 0x5151),
-                               __byte_perm((uint32_t)b[2 * r], (uint32_t)b[2 * r + 1], 0x5151), 0x5410);
-        };
+        const uint32_t k16 = intra_k16();
+        auto word = [k16](const int (&a)[4], const int (&b)[4], int r) { return intra_word_fma(a, b, r, k16); };
 #pragma unroll
         for (int m = 0; m < 2; m++) {
             uint32_t Af[2];

@@ -37,6 +37,22 @@ __device__ __forceinline__ uint32_t intra_word(const int (&a)[4], const int (&b)
                        __byte_perm((uint32_t)b[2 * r], (uint32_t)b[2 * r + 1], 0x5151), 0x5410);
 }
 
+// The same word with the shift-and-merge on the FMA pipe: every sum is < 2^16 (pixel in byte 1, remainder in byte 0), so a * 2^16 + b holds
+// the pixel of a in byte 3 and the pixel of b in byte 1 with no carry between them -- two multiply-adds (k16 = 65536 in a register the
+// compiler cannot fold, so that they stay IMADs) and ONE permute per word instead of three permutes on the integer ALU pipe, which is the
+// busiest pipe of the fractional modes (ncu: 52-76 %, profiles/r02_ncu_intra_frac.md).
+__device__ __forceinline__ uint32_t intra_word_fma(const int (&a)[4], const int (&b)[4], int r, uint32_t k16)
+{
+    const uint32_t x = (uint32_t)a[2 * r] * k16 + (uint32_t)b[2 * r], y = (uint32_t)a[2 * r + 1] * k16 + (uint32_t)b[2 * r + 1];
+    return __byte_perm(x, y, 0x5173);
+}
+__device__ __forceinline__ uint32_t intra_k16()
+{
+    uint32_t k;
+    asm volatile("mov.b32 %0, 0x10000;" : "=r"(k));
+    return k;
+}
+
 constexpr int INTRA_WARPS = 8;
 constexpr int INTRA_STRIP = 112;            // 32 (negative part) + 66 + padding, multiple of 16
 
