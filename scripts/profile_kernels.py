@@ -44,6 +44,10 @@ xb.xSatd8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, c
 xb.tune(1, 0)
 for _ in range(2):
     xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+# 16-bit cost surfaces (the u16 instantiations) and the argmin-only form of the SAD search
+xb.xSatd8x8SearchU16Dev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+xb.xSad8x8SearchU16Dev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, cost.data_ptr(), best.data_ptr(), st)
+xb.xSad8x8SearchDev(cur.data_ptr(), refp.data_ptr(), w + 64, w, h, rg, 0, nb, 0, best.data_ptr(), st)
 # round 2: inverse, fused residual + DCT32 on tiled frames, mode-major predictor, decision, the closed block loop and its Recon leg, quantiser stub
 xb.xIdct32BatchDev(src.data_ptr(), dst.data_ptr(), n, 7, 12, st)
 fw, fh = 7680, 4320 * 2 // 32 * 32
