@@ -315,6 +315,8 @@ cudaError_t launch_dct16_imma(const int16_t* src, int16_t* dst, size_t nBlocks, 
 // ------------------------------------------------------------------------------------------------
 constexpr int D8_WARPS = 8;
 
+// (Measured and not kept: the rounding shifts as the high word of a multiply by 2^(32-shift) -- IMAD.HI on the idle FMA pipe instead of SHF
+// on the busy integer-ALU pipe -- 0.996 -> 0.93 of the roofline: IMAD.HI is a multi-pass instruction.)
 __global__ void __launch_bounds__(D8_WARPS * 32, 2)
 dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t nBlocks, int shift1, int shift2)
 {
@@ -341,7 +343,16 @@ dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
     const size_t nUnits = (nPairs + 7) / 8;
     const size_t first = (size_t)blockIdx.x * D8_WARPS + warp;
     const size_t stride = (size_t)gridDim.x * D8_WARPS;
+    // a unit = 16 consecutive blocks = 2 KiB: every unit but a ragged last one is addressed from ONE base pointer with immediate offsets
+    // (the per-block clamps and 64-bit store predicates of the general form were a quarter of the kernel's integer-ALU instructions)
+    const int offL = (q >> 1) * 64 + g * 8 + (q & 1) * 4, offS = g * 8 + q * 2;
     auto load_unit = [&](size_t u, uint2 (&w)[8]) {
+        if ((u + 1) * 16 <= nBlocks) {
+            const int16_t* p = src + u * 1024 + offL;
+#pragma unroll
+            for (int pp = 0; pp < 8; pp++) w[pp] = ld_global_stream_v2(p + pp * 128);
+            return;
+        }
 #pragma unroll
         for (int pp = 0; pp < 8; pp++) {
             size_t blk = (u * 8 + pp) * 2 + (q >> 1);
@@ -361,6 +372,9 @@ dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
             BH[pp] = prmt(nxt[pp].x, nxt[pp].y, 0x7531);
         }
         if (u + stride < nUnits) load_unit(u + stride, nxt);
+        const size_t left = nBlocks - u * 16;
+        const int rem = left < 16 ? (int)left : 16;             // blocks of this unit that exist: one 32-bit compare per store
+        int16_t* dU = dst + u * 1024 + offS;
 
 #pragma unroll
         for (int pp = 0; pp < 8; pp++) {
@@ -380,9 +394,8 @@ dct8_imma_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
 #pragma unroll
             for (int c = 0; c < 4; c++) r[c] = (dl[c] + dh[c] * 256) >> shift2;
             // r0,r1: dct_alpha[k2=g][k=2q,2q+1];  r2,r3: dct_beta[k2=g][k=2q,2q+1]
-            const size_t b0 = (u * 8 + pp) * 2;
-            if (b0 < nBlocks) *reinterpret_cast<uint32_t*>(dst + b0 * 64 + g * 8 + q * 2) = prmt(r[0], r[1], 0x5410);
-            if (b0 + 1 < nBlocks) *reinterpret_cast<uint32_t*>(dst + (b0 + 1) * 64 + g * 8 + q * 2) = prmt(r[2], r[3], 0x5410);
+            if (2 * pp < rem) *reinterpret_cast<uint32_t*>(dU + pp * 128) = prmt(r[0], r[1], 0x5410);
+            if (2 * pp + 1 < rem) *reinterpret_cast<uint32_t*>(dU + pp * 128 + 64) = prmt(r[2], r[3], 0x5410);
         }
     }
 }
