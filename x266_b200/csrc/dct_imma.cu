@@ -457,23 +457,30 @@ frame_resi_dct32_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
     const size_t first = (size_t)blockIdx.x * FR_WARPS + warp;
     const size_t stride = (size_t)gridDim.x * FR_WARPS;
 
-    // lane's 8 pixels of row j = 8t+g: columns 8q..8q+7 -> tile column q>>1, in-tile offset (j&15)*16 + 8*(q&1)
-    auto load_block = [&](size_t b, uint2 (&c)[4], uint2 (&p)[4]) {
-        const size_t by = b / blocksPerRow, bx = b - by * blocksPerRow;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int j = 8 * t + g;
-            const size_t tile = (2 * by + (j >> 4)) * tilesPerRow + 2 * bx + (q >> 1);
-            const size_t off = tile * 512 + (j & 15) * 16 + 8 * (q & 1);
-            c[t] = ld_global_stream_v2(cur + off);
-            p[t] = ld_global_stream_v2(pred + off);
-        }
+    // lane's 8 pixels of row j = 8t+g: columns 8q..8q+7 -> tile column q>>1, tile row j>>4 = t>>1, in-tile offset (j&15)*16 + 8*(q&1) =
+    // (t&1)*128 + g*16 + 8*(q&1): ONE base address per block, the four rows at +0, +128, +rowStride, +rowStride+128.  The block's (bx, by)
+    // is carried along the grid stride instead of divided out of the 64-bit block index every time.
+    const unsigned bpr = (unsigned)blocksPerRow;
+    const unsigned rowStride = (unsigned)tilesPerRow * 512u;
+    const unsigned laneOff = (unsigned)(q >> 1) * 512u + (unsigned)g * 16u + 8u * (unsigned)(q & 1);
+    const unsigned sby = (unsigned)(stride / bpr), sbx = (unsigned)(stride % bpr);
+    unsigned pby = (unsigned)(first / bpr), pbx = (unsigned)(first % bpr);      // block the next prefetch loads
+    auto load_next = [&](uint2 (&c)[4], uint2 (&p)[4]) {
+        const size_t base = ((size_t)(2u * pby) * (unsigned)tilesPerRow + 2u * pbx) * 512u + laneOff;
+        const uint8_t* cb = cur + base;
+        const uint8_t* pb = pred + base;
+        c[0] = ld_global_stream_v2(cb); c[1] = ld_global_stream_v2(cb + 128);
+        c[2] = ld_global_stream_v2(cb + rowStride); c[3] = ld_global_stream_v2(cb + rowStride + 128);
+        p[0] = ld_global_stream_v2(pb); p[1] = ld_global_stream_v2(pb + 128);
+        p[2] = ld_global_stream_v2(pb + rowStride); p[3] = ld_global_stream_v2(pb + rowStride + 128);
+        pbx += sbx; pby += sby;
+        if (pbx >= bpr) { pbx -= bpr; pby++; }
     };
 
     uint2 nc[DEPTH][4] = {}, np[DEPTH][4] = {};
 #pragma unroll
     for (int d = 0; d < DEPTH; d++)
-        if (first + d * stride < nBlocks) load_block(first + d * stride, nc[d], np[d]);
+        if (first + d * stride < nBlocks) load_next(nc[d], np[d]);
 
     for (size_t b = first; b < nBlocks; b += stride) {
         uint2 bc[4], bp[4];
@@ -483,7 +490,7 @@ frame_resi_dct32_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restri
         for (int d = 0; d + 1 < DEPTH; d++)
 #pragma unroll
             for (int t = 0; t < 4; t++) { nc[d][t] = nc[d + 1][t]; np[d][t] = np[d + 1][t]; }
-        if (b + DEPTH * stride < nBlocks) load_block(b + DEPTH * stride, nc[DEPTH - 1], np[DEPTH - 1]);
+        if (b + DEPTH * stride < nBlocks) load_next(nc[DEPTH - 1], np[DEPTH - 1]);
 
         uint32_t B2L[4][2], B2H[4][2];
 #pragma unroll
