@@ -112,5 +112,20 @@ scur = rng.integers(0, 256, (16, 200)).astype(np.uint8); sref = rng.integers(0, 
 c, b = xb.xSad8x8Search(scur, sref, 32)
 wc, wb = o.sad_search(scur, sref, 32, 0, 50)
 check("sad search v2 R=32", np.array_equal(c, wc) and np.array_equal(b, wb))
+# 16-bit cost surfaces (both searches, R = 32 tile kernels and the any-range kernels), misaligned planes (byte-load prologue)
+c, b = xb.xSad8x8Search(scur, sref, 32, u16=True)
+check("sad search v2 R=32 u16 surface", np.array_equal(c, wc) and np.array_equal(b, wb))
+c, b = xb.xSatd8x8Search(scur, sref, 32, u16=True)
+wc2, wb2 = o.satd_search(scur, sref, 32, 0, 50)
+check("satd search v3 R=32 u16 surface", np.array_equal(c, wc2) and np.array_equal(b, wb2))
+s3c, s3r = rng.integers(0, 256, (16, 24)).astype(np.uint8), rng.integers(0, 256, (16 + 6, 24 + 6)).astype(np.uint8)
+c, b = xb.xSatd8x8Search(s3c, s3r, 3, u16=True)
+wc3, wb3 = o.satd_search(s3c, s3r, 3, 0, 6)
+check("satd search any-range R=3 u16 surface", np.array_equal(c, wc3) and np.array_equal(b, wb3))
+c, b = xb.xSad8x8Search(s3c, s3r, 3, u16=True)
+wc3, wb3 = o.sad_search(s3c, s3r, 3, 0, 6)
+check("sad search any-range R=3 u16 surface", np.array_equal(c, wc3) and np.array_equal(b, wb3))
+xs8 = o.residual(1237 * 64 + 64 * 5, 4, 2)           # DCT8: 1242 blocks = 77 full units + a ragged one of 10
+check("dct8 ragged tail", np.array_equal(xb.xDctNBatch(3, xs8, 2, 9), o.dct(xs8.reshape(-1, 8, 8), 3, 2, 9).ravel()))
 print("ALL OK" if ok else "SOME FAILED")
 sys.exit(0 if ok else 1)
