@@ -40,6 +40,9 @@ for rep, out in (("prof_all.ncu-rep", f"{tag}_ncu_summary.md"), ("prof_dct32_ben
     if os.path.exists(rp):
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rp], capture_output=True, text=True).stdout
         open(os.path.join(P, out), "w").write(txt.replace(G + "/", "gpurun_out/"))
+    elif rep == "prof_all.ncu-rep" and os.path.exists(os.path.join(G, "ncu_summary_all.md")):
+        # the report was too large to travel back: scripts/gpu_profile.sh made the summary on the GPU box
+        shutil.copy(os.path.join(G, "ncu_summary_all.md"), os.path.join(P, out))
 
 # 3. DRAM traffic of the bench-size DCT32 launch
 rp = os.path.join(G, "prof_dct32_benchsize.ncu-rep")

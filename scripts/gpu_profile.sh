@@ -11,4 +11,7 @@ ncu --set full --clock-control none --import-source on -k regex:"dct32_imma" -s 
 ncu --set full --clock-control none -k regex:"dct|satd8x8|intra32|sad8x8|quant|tiles_to" -s 0 -c 80 \
     -o gpurun_out/prof_all -f python scripts/profile_kernels.py 16 > gpurun_out/ncu_all.log 2>&1
 tail -3 gpurun_out/ncu_all.log
+# the per-kernel summary is made here (ncu CLI only); the report itself travels back only if it fits gpurun's 64 MiB return limit
+python scripts/ncu_summary.py gpurun_out/prof_all.ncu-rep > gpurun_out/ncu_summary_all.md 2> gpurun_out/ncu_summary_all.err
+if [ $(stat -c %s gpurun_out/prof_all.ncu-rep) -gt 50000000 ]; then rm -f gpurun_out/prof_all.ncu-rep; echo "prof_all.ncu-rep dropped (summary kept)"; fi
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches.csv

@@ -14,7 +14,7 @@ dst = torch.empty_like(src)
 st = torch.cuda.current_stream().cuda_stream
 for v in (xb.DCT_IMMA, xb.DCT_BFLY):
     xb.set_dct_variant(v)
-    for _ in range(3):
+    for _ in range(2):
         xb.xDct32BatchDev(src.data_ptr(), dst.data_ptr(), n, 6, 11, st)
 for log2n, (s1, s2) in ((2, (1, 8)), (3, (2, 9)), (4, (3, 10))):
     xb.xDctNBatchDev(log2n, src.data_ptr(), dst.data_ptr(), (n * 1024) >> (2 * log2n), s1, s2, st)
