@@ -568,8 +568,8 @@ def secondary_section(env, src, dst, n_blocks, cpu):
         secondary.append(env.hbm_entry(f"dct{1 << log2n}_blocks_per_s", ns >> (2 * log2n), 4 << (2 * log2n), ms))
     ms = env.timed(lambda: xb.xIdct32BatchDev(sp, dp, ns >> 10, 7, 10, st), 10)
     secondary.append(env.hbm_entry("idct32_blocks_per_s", ns >> 10, 4096, ms, "parity unpinned (no inverse in the reference)"))
-    # N2: fused residual + DCT32 straight from ref_block_t-tiled current / prediction frames (8 stacked 8K luma frames, one launch)
-    fw, fh = 7680, 4320 * 8
+    # N2: fused residual + DCT32 straight from ref_block_t-tiled current / prediction frames (16 stacked 8K luma frames, one launch)
+    fw, fh = 7680, 4320 * 16
     ntile = (fw // 16) * (fh // 16)
     if (fw // 32) * (fh // 32) * 1024 <= dst.numel():
         fcur = torch.randint(0, 256, (ntile * 512,), device=dev, generator=g, dtype=torch.uint8)
@@ -577,7 +577,7 @@ def secondary_section(env, src, dst, n_blocks, cpu):
         nfb = (fw // 32) * (fh // 32)
         ms = env.timed(lambda: xb.xFrameResiDct32Dev(fcur.data_ptr(), fprd.data_ptr(), fw, fh, dp, 4, 11, st), 10)
         secondary.append(env.hbm_entry("frame_resi_dct32_blocks_per_s", nfb, 4096, ms,
-                                       "xFrameResiDct32: 8 stacked 8K frames of ref_block_t tiles (cur, pred) -> coefficients; 2 KB of luma in + 2 KB out per block"))
+                                       "xFrameResiDct32: 16 stacked 8K frames of ref_block_t tiles (cur, pred) -> coefficients; 2 KB of luma in + 2 KB out per block"))
         del fcur, fprd
     npred = 1 << 20
     refs = torch.randint(0, 256, (npred, 129), device=dev, generator=g, dtype=torch.uint8)
