@@ -579,6 +579,13 @@ def test_search_u16_cost_surface(x266, orc, rng_px):
     assert (c == 16320).all()
     c, _ = x266.xSatd8x8Search(zero, full, rng_px, u16=True)
     assert (c == 4080).all()
+    # the largest SATD an 8-bit search can produce: +-255 in a bent pattern (flat Hadamard spectrum) = 32640, still a uint16_t
+    from test_oracle import bent_block
+    pat = np.where(np.tile(bent_block(), (2, 4)) > 0, 255, 0).astype(np.uint8)                  # 16 x 32, aligned to the block grid
+    inv = np.pad(255 - pat, rng_px, mode="wrap") if rng_px % 8 == 0 else np.pad(255 - pat, rng_px, mode="edge")
+    c, _ = x266.xSatd8x8Search(pat, inv, rng_px, u16=True)
+    wc, _ = orc.satd_search(pat, inv, rng_px, 0, 8)
+    assert np.array_equal(c, wc) and c[:, rng_px, rng_px].max() == 32640 and c.max() == 32640
     # device forms, misaligned cost pointer (2-byte aligned only), and the tiled device forms
     w, h = 72, 40
     side, nb = 2 * rng_px + 1, 45

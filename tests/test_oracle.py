@@ -116,6 +116,29 @@ def test_small_dct_pinned_through_reference(orc, ref, log2n):
             assert (orc.partial(rows, shift, line, log2n, dense=True).reshape(n, line) == want).all()
 
 
+def bent_block():
+    """8x8 pattern of +-1 whose 2-D Hadamard transform is flat (|T_k| = 8 for all 64 k): the bent function x0x1 ^ x2x3 ^ x4x5 of the
+    6 sample-index bits.  255 * pattern is the 8-bit difference block with the largest possible SATD."""
+    p = np.arange(64)
+    f = ((p & 1) & (p >> 1 & 1)) ^ ((p >> 2 & 1) & (p >> 3 & 1)) ^ ((p >> 4 & 1) & (p >> 5 & 1))
+    return (1 - 2 * f).reshape(8, 8)
+
+
+def test_satd_of_8bit_pixels_fits_16_bits(orc, ref):
+    """The bound behind the 16-bit cost surface (xSatd8x8SearchU16): sum |T_k| <= sqrt(64) ||T||_2 = 64 ||x||_2 <= 64 * 8 * 255 = 130560, so the cost
+    (sum + 2) >> 2 <= 32640 -- and the bound is attained by +-255 in a bent pattern, through the reference satd8x8 itself (src_tb/satd.c:31-118)."""
+    d = (255 * bent_block()).astype(np.int16)
+    assert orc.satd(d)[0] == 32640 and ref.satd(d)[0] == 32640
+    rng = np.random.default_rng(16)
+    worst = 0
+    for _ in range(20):
+        x = rng.choice([-255, 255], (4096, 64)).astype(np.int16)
+        worst = max(worst, int(orc.satd(x).max()))
+    assert worst <= 32640
+    sad_max = 64 * 255
+    assert sad_max == 16320 < 65536
+
+
 def test_satd_search_oracle_is_satd_of_differences(orc):
     rng = np.random.default_rng(3)
     h, w, r = 16, 24, 3
