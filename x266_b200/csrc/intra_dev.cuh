@@ -132,9 +132,9 @@ constexpr int IDEC_WARPS = 8;
 
 struct DecideSmem {
     __align__(16) uint8_t scur[2][1024];                 // [0] = block, [1] = its transpose
-    __align__(16) int stc[2][32 * 32];                   // T(cur), T(cur^T) in accumulator layout
+    __align__(16) int stc[2][32 * 32];                   // T(cur), T(cur^T) in accumulator layout: [n-tile t][lane][register c], one 16-byte read per tile
     __align__(16) uint8_t sraw[144];
-    __align__(16) uint8_t strip[IDEC_WARPS][INTRA_STRIP + 16];
+    __align__(16) uint8_t strip[IDEC_WARPS][2][INTRA_STRIP + 16];   // per warp: [0] the left-based working line (modes 2..17), [1] the top-based one
     uint32_t scost[35];
 };
 
@@ -166,8 +166,7 @@ __device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)
     // this lane's rows: sub-blocks g and g+8 (same column band sx), sub-block rows q and 4+q
     const int sx = (g & 3) * 8;
     const int syA = (g >> 2) * 8, syB = syA + 16;
-    uint8_t* sref = sm.strip[warp] + 32 + 4;            // sref[i] = ref[i]; +4 keeps sref-32 word aligned
-    const uint32_t* strip32 = reinterpret_cast<const uint32_t*>(sm.strip[warp]);
+    // sref[i] = ref[i] at byte 36 of a strip (+4 keeps sref-32 word aligned)
 
     {
         const uint32_t w = reinterpret_cast<const uint32_t*>(curBlock)[tid];
@@ -191,25 +190,30 @@ __device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)
             int d[4];
             mma_u8s8(d, A[0], B[0][t][0], B[0][t][1], cZero);
             mma_u8s8(d, A[1], B[1][t][0], B[1][t][1], d);
-#pragma unroll
-            for (int c = 0; c < 4; c++) sm.stc[warp][(t * 4 + c) * 32 + lane] = d[c];
+            *reinterpret_cast<int4*>(&sm.stc[warp][(t * 32 + lane) * 4]) = make_int4(d[0], d[1], d[2], d[3]);
         }
     }
     __syncthreads();
     const uint8_t* left = sm.sraw;
     const uint8_t* top = sm.sraw + 64;
+    // both working lines of this warp, staged ONCE per block (they used to be rebuilt for every mode); a negative-angle mode only rewrites
+    // the projected part ref[-|angle|..-1], which is all it reads below ref[0]
+    for (int i = lane; i <= 71; i += 32) {
+        sm.strip[warp][1][36 + i] = i > 64 ? (uint8_t)0 : top[i];
+        sm.strip[warp][0][36 + i] = i > 64 ? (uint8_t)0 : (i == 0 ? top[0] : left[i - 1]);
+    }
+    __syncwarp();
 
     for (int mode = warp; mode < 35; mode += IDEC_WARPS) {
         const bool isVer = mode >= 18;
         const int ang = c_intraAngle[mode];
+        uint8_t* sref = sm.strip[warp][isVer ? 1 : 0] + 32 + 4;
+        const uint32_t* strip32 = reinterpret_cast<const uint32_t*>(sm.strip[warp][isVer ? 1 : 0]);
         uint32_t A[2][4];
         if (mode >= 2) {
-            __syncwarp();
-            for (int i = lane; i <= 71; i += 32) sref[i] = i > 64 ? (uint8_t)0 : (isVer ? top[i] : (i == 0 ? top[0] : left[i - 1]));
             if (ang < 0) {
-                int inv = 0;
-#pragma unroll
-                for (int a = 0; a < 8; a++) if (c_intraAngle[11 + a] == ang) inv = c_intraInv[a];
+                const int inv = c_intraInvMode[mode];
+                __syncwarp();
                 const int k = lane + 1;
                 if (-k >= ang) {
                     const int sidx = (k * inv + 128) >> 8;
@@ -261,10 +265,11 @@ __device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)
             int d[4];
             mma_u8s8(d, A[0], B[0][t][0], B[0][t][1], cZero);
             mma_u8s8(d, A[1], B[1][t][0], B[1][t][1], d);
-            sa0 = __sad(d[0], tc[(t * 4 + 0) * 32 + lane], sa0);
-            sa1 = __sad(d[1], tc[(t * 4 + 1) * 32 + lane], sa1);
-            sb0 = __sad(d[2], tc[(t * 4 + 2) * 32 + lane], sb0);
-            sb1 = __sad(d[3], tc[(t * 4 + 3) * 32 + lane], sb1);
+            const int4 c4v = *reinterpret_cast<const int4*>(&tc[(t * 32 + lane) * 4]);
+            sa0 = __sad(d[0], c4v.x, sa0);
+            sa1 = __sad(d[1], c4v.y, sa1);
+            sb0 = __sad(d[2], c4v.z, sb0);
+            sb1 = __sad(d[3], c4v.w, sb1);
         }
         unsigned sadA = sa0 + sa1, sadB = sb0 + sb1;                // sub-blocks g and g+8, partial over this lane's columns
         sadA += __shfl_xor_sync(0xffffffffu, sadA, 1); sadB += __shfl_xor_sync(0xffffffffu, sadB, 1);
