@@ -8,7 +8,7 @@
 // come in and 2 KiB of levels + 1 KiB of reconstruction + the mode go out; the prediction, the residual, the coefficients and
 // the de-quantised coefficients never leave the SM.
 //
-// A CTA of 8 warps takes 8 consecutive blocks: the decision of each block is made by the whole CTA (decide_block, intra_dev.cuh:
+// A CTA of 8 warps takes 8 consecutive blocks: the decision of each pair of blocks is made by the whole CTA (decide_blocks, intra_dev.cuh:
 // one warp per mode, 16 IMMA per mode), then every warp reconstructs one of the 8 blocks on its own (encode_block_warp below: the
 // register-resident byte-plane IMMA choreography of dct_imma.cu, forward with the residual formed by linearity
 // G*(c - p) = G*c + (-G)*p on raw pixels, inverse from a per-warp shared-memory tile).  intra32_recon_kernel is the `Recon`
@@ -320,21 +320,23 @@ intra32_encode_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
     EncodeSmem& sm = *reinterpret_cast<EncodeSmem*>(smemRaw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t nGroups = (n + ENC_WARPS - 1) / ENC_WARPS;
+    static_assert(ENC_WARPS % IDEC_NB == 0, "a group of blocks is a whole number of decision passes");
+    DecideIn in;                                                  // inputs of the next decision pass (registers), loaded one pass ahead
+    decide_load(in, cur, refs, (size_t)blockIdx.x * ENC_WARPS, n, tid);
     for (size_t grp = blockIdx.x; grp < nGroups; grp += gridDim.x) {
         {
             uint32_t B[2][8][2];                                  // +-1 fragments: live only during the decision phase
             decide_hadamard_fragments(B, lane >> 2, lane & 3);
-            for (int i = 0; i < ENC_WARPS; i++) {
+            for (int i = 0; i < ENC_WARPS; i += IDEC_NB) {
                 const size_t p = grp * ENC_WARPS + i;
+                // the pass after this one: the next blocks of this group, or the first blocks of this CTA's next group (past the end: loads nothing)
+                const size_t pNext = i + IDEC_NB < ENC_WARPS ? p + IDEC_NB : (grp + gridDim.x) * ENC_WARPS;
                 if (p >= n) break;
-                decide_block(sm.dec, B, cur + p * 1024, refs + p * 129, tid);
-                if (cost && tid < 35) cost[p * 35 + tid] = sm.dec.scost[tid];
-                if (tid == 0) {
-                    unsigned bc = sm.dec.scost[0];
-                    int bm = 0;
-                    for (int m = 1; m < 35; m++) if (sm.dec.scost[m] < bc) { bc = sm.dec.scost[m]; bm = m; }
-                    sm.best[i] = bm;
-                    bestMode[p] = bm;
+                const int nblk = (n - p) < (size_t)IDEC_NB ? (int)(n - p) : IDEC_NB;
+                decide_blocks(sm.dec, B, in, nblk, cur, refs, pNext, n, tid);
+                if (warp < nblk) {
+                    const int bm = decide_output(sm.dec, warp, cost ? cost + (p + warp) * 35 : nullptr, lane);
+                    if (lane == 0) { sm.best[i + warp] = bm; bestMode[p + warp] = bm; }
                 }
             }
         }

@@ -571,19 +571,22 @@ intra32_decide_v2_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restr
                          int32_t* __restrict__ bestMode, size_t n)
 {
     __shared__ DecideSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t B[2][8][2];
     decide_hadamard_fragments(B, lane >> 2, lane & 3);
-    for (size_t p = blockIdx.x; p < n; p += gridDim.x) {
-        decide_block(sm, B, cur + p * 1024, refs + p * 129, tid);
-        if (tid < 35) cost[p * 35 + tid] = sm.scost[tid];
-        if (tid == 0) {
-            unsigned bc = sm.scost[0];
-            int bm = 0;
-            for (int m = 1; m < 35; m++) if (sm.scost[m] < bc) { bc = sm.scost[m]; bm = m; }
-            bestMode[p] = bm;
+    // a pass = IDEC_NB consecutive blocks: 70 (block, mode) items over the 8 warps; the inputs of the next pass are loaded during this one
+    const size_t stride = (size_t)gridDim.x * IDEC_NB;
+    size_t p = (size_t)blockIdx.x * IDEC_NB;
+    DecideIn in;
+    decide_load(in, cur, refs, p, n, tid);
+    for (; p < n; p += stride) {
+        const int nblk = (n - p) < (size_t)IDEC_NB ? (int)(n - p) : IDEC_NB;
+        decide_blocks(sm, B, in, nblk, cur, refs, p + stride, n, tid);
+        if (warp < nblk) {
+            const int bm = decide_output(sm, warp, cost + (p + warp) * 35, lane);
+            if (lane == 0) bestMode[p + warp] = bm;
         }
-        __syncthreads();
+        // no barrier here: the next pass writes scost only after its own two barriers, and scur / sraw are not read after decide_blocks' last one
     }
 }
 
@@ -593,7 +596,8 @@ cudaError_t launch_intra32_decide(const uint8_t* cur, const uint8_t* refs, uint3
 {
     if (n == 0) return cudaSuccess;
     const size_t cap = (size_t)sm_count() * resident_ctas_per_sm((const void*)intra32_decide_v2_kernel, IDEC_WARPS * 32, 0);
-    intra32_decide_v2_kernel<<<(unsigned)(n < cap ? n : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
+    const size_t passes = (n + IDEC_NB - 1) / IDEC_NB;
+    intra32_decide_v2_kernel<<<(unsigned)(passes < cap ? passes : cap), IDEC_WARPS * 32, 0, st>>>(cur, refs, cost, bestMode, n);
     count_launch();
     return cudaGetLastError();
 }

@@ -129,14 +129,31 @@ __device__ __forceinline__ void intra_angular_rows(const uint32_t* __restrict__ 
 // holds the 35 costs.
 // ------------------------------------------------------------------------------------------------
 constexpr int IDEC_WARPS = 8;
+constexpr int IDEC_NB = 2;                               // blocks decided per pass of a CTA: 70 (block, mode) items over 8 warps (35 leave 3 warps a mode short)
 
 struct DecideSmem {
-    __align__(16) uint8_t scur[2][1024];                 // [0] = block, [1] = its transpose
-    __align__(16) int stc[2][32 * 32];                   // T(cur), T(cur^T) in accumulator layout: [n-tile t][lane][register c], one 16-byte read per tile
-    __align__(16) uint8_t sraw[144];
-    __align__(16) uint8_t strip[IDEC_WARPS][2][INTRA_STRIP + 16];   // per warp: [0] the left-based working line (modes 2..17), [1] the top-based one
-    uint32_t scost[35];
+    __align__(16) uint8_t scur[IDEC_NB][2][1024];        // per block: [0] = block, [1] = its transpose
+    __align__(16) int stc[IDEC_NB][2][32 * 32];          // T(cur), T(cur^T) in accumulator layout: [n-tile t][lane][register c], one 16-byte read per tile
+    __align__(16) uint8_t sraw[IDEC_NB][144];
+    __align__(16) uint8_t strip[IDEC_WARPS][IDEC_NB][2][INTRA_STRIP + 16];   // per warp and block: [0] the left-based working line (modes 2..17), [1] the top-based one
+    uint32_t scost[IDEC_NB][35];
 };
+
+// the inputs of one pass in registers (thread tid: word tid of each current block, byte tid of each block's 129 reference bytes), loaded
+// one pass ahead so that a CTA never waits on HBM at the top of a block
+struct DecideIn { uint32_t w[IDEC_NB]; uint32_t r[IDEC_NB]; };
+
+__device__ __forceinline__ void decide_load(DecideIn& in, const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refs, size_t p, size_t n, int tid)
+{
+#pragma unroll
+    for (int b = 0; b < IDEC_NB; b++) {
+        in.w[b] = 0; in.r[b] = 0;
+        if (p + b < n) {
+            in.w[b] = __ldg(reinterpret_cast<const uint32_t*>(cur + (p + b) * 1024) + tid);
+            if (tid < 129) in.r[b] = __ldg(refs + (p + b) * 129 + tid);
+        }
+    }
+}
 
 // +-1 matrix fragments, identical to satd8x8_imma_kernel: K position 16r+4q+i <-> sample 32s+8q+4r+i, column 8t+g
 __device__ __forceinline__ void decide_hadamard_fragments(uint32_t (&B)[2][8][2], int g, int q)
@@ -157,8 +174,10 @@ __device__ __forceinline__ void decide_hadamard_fragments(uint32_t (&B)[2][8][2]
             }
 }
 
-__device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)[2][8][2], const uint8_t* __restrict__ curBlock,
-                                             const uint8_t* __restrict__ refsBlock, int tid)
+// Decides blocks p .. p+nblk-1 (nblk <= IDEC_NB) whose inputs are in `in`, then reloads `in` with the blocks at pNext (if any) while the modes run.
+// On return (after a CTA barrier) sm.scost[b][0..34] holds the 35 costs of block b.
+__device__ __forceinline__ void decide_blocks(DecideSmem& sm, const uint32_t (&B)[2][8][2], DecideIn& in, int nblk,
+                                              const uint8_t* __restrict__ cur, const uint8_t* __restrict__ refs, size_t pNext, size_t n, int tid)
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
@@ -166,23 +185,29 @@ __device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)
     // this lane's rows: sub-blocks g and g+8 (same column band sx), sub-block rows q and 4+q
     const int sx = (g & 3) * 8;
     const int syA = (g >> 2) * 8, syB = syA + 16;
-    // sref[i] = ref[i] at byte 36 of a strip (+4 keeps sref-32 word aligned)
 
     {
-        const uint32_t w = reinterpret_cast<const uint32_t*>(curBlock)[tid];
-        reinterpret_cast<uint32_t*>(sm.scur[0])[tid] = w;
         const int row = tid >> 3, c0 = (tid & 7) * 4;
 #pragma unroll
-        for (int i = 0; i < 4; i++) sm.scur[1][(c0 + i) * 32 + row] = (uint8_t)(w >> (8 * i));
-        if (tid < 129) sm.sraw[tid] = refsBlock[tid];
+        for (int b = 0; b < IDEC_NB; b++) {
+            if (b < nblk) {
+                const uint32_t w = in.w[b];
+                reinterpret_cast<uint32_t*>(sm.scur[b][0])[tid] = w;
+#pragma unroll
+                for (int i = 0; i < 4; i++) sm.scur[b][1][(c0 + i) * 32 + row] = (uint8_t)(w >> (8 * i));
+                if (tid < 129) sm.sraw[b][tid] = (uint8_t)in.r[b];
+            }
+        }
     }
     __syncthreads();
-    if (warp < 2) {                               // T(cur) (warp 0) and T(cur^T) (warp 1)
+    decide_load(in, cur, refs, pNext, n, tid);            // the next pass's inputs travel while this pass computes
+    if (warp < 2 * nblk) {                                // T(cur) and T(cur^T) of block warp >> 1
+        const int b = warp >> 1, tr = warp & 1;
         uint32_t A[2][4];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const uint2 ra = *reinterpret_cast<const uint2*>(&sm.scur[warp][(syA + 4 * s + q) * 32 + sx]);
-            const uint2 rb = *reinterpret_cast<const uint2*>(&sm.scur[warp][(syB + 4 * s + q) * 32 + sx]);
+            const uint2 ra = *reinterpret_cast<const uint2*>(&sm.scur[b][tr][(syA + 4 * s + q) * 32 + sx]);
+            const uint2 rb = *reinterpret_cast<const uint2*>(&sm.scur[b][tr][(syB + 4 * s + q) * 32 + sx]);
             A[s][0] = ra.x; A[s][2] = ra.y; A[s][1] = rb.x; A[s][3] = rb.y;
         }
 #pragma unroll
@@ -190,25 +215,31 @@ __device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)
             int d[4];
             mma_u8s8(d, A[0], B[0][t][0], B[0][t][1], cZero);
             mma_u8s8(d, A[1], B[1][t][0], B[1][t][1], d);
-            *reinterpret_cast<int4*>(&sm.stc[warp][(t * 32 + lane) * 4]) = make_int4(d[0], d[1], d[2], d[3]);
+            *reinterpret_cast<int4*>(&sm.stc[b][tr][(t * 32 + lane) * 4]) = make_int4(d[0], d[1], d[2], d[3]);
+        }
+    }
+    // both working lines of this warp for every block of the pass, staged ONCE per block (they used to be rebuilt for every mode); a
+    // negative-angle mode only rewrites the projected part ref[-|angle|..-1], which is all it reads below ref[0]
+    for (int b = 0; b < nblk; b++) {
+        const uint8_t* left = sm.sraw[b];
+        const uint8_t* top = sm.sraw[b] + 64;
+        for (int i = lane; i <= 71; i += 32) {
+            sm.strip[warp][b][1][36 + i] = i > 64 ? (uint8_t)0 : top[i];
+            sm.strip[warp][b][0][36 + i] = i > 64 ? (uint8_t)0 : (i == 0 ? top[0] : left[i - 1]);
         }
     }
     __syncthreads();
-    const uint8_t* left = sm.sraw;
-    const uint8_t* top = sm.sraw + 64;
-    // both working lines of this warp, staged ONCE per block (they used to be rebuilt for every mode); a negative-angle mode only rewrites
-    // the projected part ref[-|angle|..-1], which is all it reads below ref[0]
-    for (int i = lane; i <= 71; i += 32) {
-        sm.strip[warp][1][36 + i] = i > 64 ? (uint8_t)0 : top[i];
-        sm.strip[warp][0][36 + i] = i > 64 ? (uint8_t)0 : (i == 0 ? top[0] : left[i - 1]);
-    }
-    __syncwarp();
 
-    for (int mode = warp; mode < 35; mode += IDEC_WARPS) {
+    // the (block, mode) items of the pass, round-robin over the warps
+    for (int item = warp; item < 35 * nblk; item += IDEC_WARPS) {
+        const int b = item >= 35 ? 1 : 0;
+        const int mode = item - 35 * b;
+        const uint8_t* left = sm.sraw[b];
+        const uint8_t* top = sm.sraw[b] + 64;
         const bool isVer = mode >= 18;
         const int ang = c_intraAngle[mode];
-        uint8_t* sref = sm.strip[warp][isVer ? 1 : 0] + 32 + 4;
-        const uint32_t* strip32 = reinterpret_cast<const uint32_t*>(sm.strip[warp][isVer ? 1 : 0]);
+        uint8_t* sref = sm.strip[warp][b][isVer ? 1 : 0] + 32 + 4;     // sref[i] = ref[i] at byte 36 of a strip (+4 keeps sref-32 word aligned)
+        const uint32_t* strip32 = reinterpret_cast<const uint32_t*>(sm.strip[warp][b][isVer ? 1 : 0]);
         uint32_t A[2][4];
         if (mode >= 2) {
             if (ang < 0) {
@@ -258,7 +289,7 @@ __device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)
                 }
         }
         // T(pred) for the 16 sub-blocks, |T(cur) - T(pred)| against the parked transform (transposed one for 2..17)
-        const int* tc = sm.stc[(mode >= 2 && !isVer) ? 1 : 0];
+        const int* tc = sm.stc[b][(mode >= 2 && !isVer) ? 1 : 0];
         unsigned sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
 #pragma unroll
         for (int t = 0; t < 8; t++) {
@@ -277,9 +308,25 @@ __device__ __forceinline__ void decide_block(DecideSmem& sm, const uint32_t (&B)
         unsigned c4 = q == 0 ? ((sadA + 2) >> 2) + ((sadB + 2) >> 2) : 0u;
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) c4 += __shfl_xor_sync(0xffffffffu, c4, o);
-        if (lane == 0) sm.scost[mode] = c4;
+        if (lane == 0) sm.scost[b][mode] = c4;
     }
     __syncthreads();
+}
+
+// After decide_blocks: warp b (b < nblk) writes block b's 35 costs (if wanted) and returns its best mode in every lane -- the smallest cost, ties to the
+// smallest mode (key = cost * 64 + mode; a cost is < 2^20), folded with shuffles instead of a 35-step scan by one thread.
+__device__ __forceinline__ int decide_output(const DecideSmem& sm, int b, uint32_t* __restrict__ costOut, int lane)
+{
+    const uint32_t c0 = sm.scost[b][lane], c1 = lane < 3 ? sm.scost[b][32 + lane] : 0u;
+    if (costOut) {
+        costOut[lane] = c0;
+        if (lane < 3) costOut[32 + lane] = c1;
+    }
+    uint32_t key = c0 * 64u + (uint32_t)lane;
+    if (lane < 3) key = min(key, c1 * 64u + 32u + (uint32_t)lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    return (int)(key & 63u);
 }
 
 } // namespace x266
