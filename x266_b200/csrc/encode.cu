@@ -61,18 +61,33 @@ constexpr int ENC_WARPS = IDEC_WARPS;
 struct EncodeWarpSmem {
     __align__(16) uint8_t pred[32 * 32];         // best-mode prediction, row-major
     __align__(16) int16_t coef[32 * 32];         // de-quantised coefficients, row-major (input of the inverse transform)
-    __align__(16) uint8_t raw[144];              // left[64] | top[65]
+    __align__(16) uint8_t raw[2][144];           // left[64] | top[65] of this block and of the warp's next one, each as the aligned words that cover it
     __align__(16) uint8_t strip[INTRA_STRIP + 16];
 };
 
 // 32x32 prediction of `mode` into ws.pred (one warp).  Angular rows come from the SWAR generator of the predictor kernel
 // (intra_angular_rows: the vertical-family prediction P_v of the main reference); horizontal modes are P_v^T.
-__device__ __forceinline__ void predict_to_tile(EncodeWarpSmem& ws, const uint8_t* __restrict__ refsBlock, int mode, int lane)
+// The 129 reference bytes of a block travel into ws.raw[buf] ahead of their use, with no register staging: when the refs array is 4-byte aligned
+// the 33 aligned words that cover [refsBlock, refsBlock + 129) are copied asynchronously (the bytes then start at offset (address & 3) of the buffer);
+// the last block of the array, whose covering words may end past it, and unaligned arrays are copied byte by byte.  Always commits one group.
+__device__ __forceinline__ int stage_refs(EncodeWarpSmem& ws, int buf, const uint8_t* __restrict__ refsBlock, bool wordsOk, int lane)
 {
-    for (int i = lane; i < 129; i += 32) ws.raw[i] = refsBlock[i];
-    __syncwarp();
-    const uint8_t* left = ws.raw;
-    const uint8_t* top = ws.raw + 64;
+    const int a = wordsOk ? (int)(reinterpret_cast<uintptr_t>(refsBlock) & 3) : 0;
+    if (wordsOk) {
+        const uint8_t* src = refsBlock - a;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ws.raw[buf]);
+        cp_async4(dst + 4u * lane, src + 4 * lane);
+        if (lane == 0) cp_async4(dst + 128u, src + 128);
+    } else {
+        for (int i = lane; i < 129; i += 32) ws.raw[buf][i] = refsBlock[i];
+    }
+    cp_async_commit();
+    return a;
+}
+
+__device__ __forceinline__ void predict_to_tile(EncodeWarpSmem& ws, const uint8_t* __restrict__ left, int mode, int lane)
+{
+    const uint8_t* top = left + 64;                               // left = the block's 129 reference bytes in shared memory (complete and visible)
     uint32_t* pred32 = reinterpret_cast<uint32_t*>(ws.pred);
     if (mode >= 2) {
         const bool isVer = mode >= 18;
@@ -127,7 +142,7 @@ __device__ __forceinline__ void predict_to_tile(EncodeWarpSmem& ws, const uint8_
 }
 
 // One warp: prediction of `mode` -> residual -> DCT32 (4/11) -> quant -> level out; dequant -> IDCT32 (7/12) -> recon out.
-__device__ __forceinline__ void encode_block_warp(EncodeWarpSmem& ws, const uint8_t* __restrict__ curBlock, const uint8_t* __restrict__ refsBlock,
+__device__ __forceinline__ void encode_block_warp(EncodeWarpSmem& ws, const uint8_t* __restrict__ curBlock, const uint8_t* __restrict__ refsSmem,
                                                   int mode, const QuantParams qp, int16_t* __restrict__ level, uint8_t* __restrict__ recon, int lane)
 {
     const int g = lane >> 2, q = lane & 3;
@@ -136,7 +151,7 @@ __device__ __forceinline__ void encode_block_warp(EncodeWarpSmem& ws, const uint
     uint2 bc[4];
 #pragma unroll
     for (int t = 0; t < 4; t++) bc[t] = *reinterpret_cast<const uint2*>(curBlock + (8 * t + g) * 32 + 8 * q);
-    predict_to_tile(ws, refsBlock, mode, lane);
+    predict_to_tile(ws, refsSmem, mode, lane);
 
     // ---- forward transform, src_tb/dct32.c:197-198 with shifts 4 / 11 on (cur - pred): the choreography of frame_resi_dct32_kernel
     {
@@ -323,7 +338,11 @@ intra32_encode_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
     static_assert(ENC_WARPS % IDEC_NB == 0, "a group of blocks is a whole number of decision passes");
     DecideIn in;                                                  // inputs of the next decision pass (registers), loaded one pass ahead
     decide_load(in, cur, refs, (size_t)blockIdx.x * ENC_WARPS, n, tid);
+    const bool refsWords = (reinterpret_cast<uintptr_t>(refs) & 3) == 0;
     for (size_t grp = blockIdx.x; grp < nGroups; grp += gridDim.x) {
+        // this warp's own block: its reference bytes travel into shared memory while the CTA decides
+        const size_t pw = grp * ENC_WARPS + warp;
+        const int ra = pw < n ? stage_refs(sm.w[warp], 0, refs + pw * 129, refsWords && pw + 1 < n, lane) : 0;
         {
             uint32_t B[2][8][2];                                  // +-1 fragments: live only during the decision phase
             decide_hadamard_fragments(B, lane >> 2, lane & 3);
@@ -340,9 +359,9 @@ intra32_encode_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict
                 }
             }
         }
+        cp_async_wait<0>();
         __syncthreads();
-        const size_t p = grp * ENC_WARPS + warp;
-        if (p < n) encode_block_warp(sm.w[warp], cur + p * 1024, refs + p * 129, sm.best[warp], qp, level + p * 1024, recon + p * 1024, lane);
+        if (pw < n) encode_block_warp(sm.w[warp], cur + pw * 1024, sm.w[warp].raw[0] + ra, sm.best[warp], qp, level + pw * 1024, recon + pw * 1024, lane);
         __syncthreads();
     }
 }
@@ -354,9 +373,25 @@ intra32_recon_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict_
 {
     __shared__ EncodeWarpSmem ws[ENC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (size_t p = (size_t)blockIdx.x * ENC_WARPS + warp; p < n; p += (size_t)gridDim.x * ENC_WARPS) {
-        const int m = mode[p];
-        encode_block_warp(ws[warp], cur + p * 1024, refs + p * 129, m > 34 ? 1 : m, qp, level + p * 1024, recon + p * 1024, lane);
+    // the reference bytes and the mode of the warp's NEXT block are in flight while this one is reconstructed (ncu on the first form: 30 % of
+    // the stall samples were long_scoreboard on the reference bytes at the top of a block)
+    const bool refsWords = (reinterpret_cast<uintptr_t>(refs) & 3) == 0;
+    const size_t stride = (size_t)gridDim.x * ENC_WARPS;
+    size_t p = (size_t)blockIdx.x * ENC_WARPS + warp;
+    if (p >= n) return;
+    int buf = 0;
+    int a = stage_refs(ws[warp], 0, refs + p * 129, refsWords && p + 1 < n, lane);
+    int m = mode[p];
+    for (; p < n; p += stride) {
+        const size_t pn = p + stride;
+        int an = 0, mn = 1;
+        if (pn < n) { an = stage_refs(ws[warp], buf ^ 1, refs + pn * 129, refsWords && pn + 1 < n, lane); mn = mode[pn]; }
+        else cp_async_commit();
+        cp_async_wait<1>();                      // everything but the group just committed: this block's bytes have landed
+        __syncwarp();
+        encode_block_warp(ws[warp], cur + p * 1024, ws[warp].raw[buf] + a, m > 34 ? 1 : m, qp, level + p * 1024, recon + p * 1024, lane);
+        __syncwarp();                            // all lanes are done with raw[buf] before the iteration after next stages into it
+        buf ^= 1; a = an; m = mn;
     }
 }
 
