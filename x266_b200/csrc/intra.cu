@@ -192,8 +192,8 @@ __device__ __forceinline__ void intra_generate(int mode, uint8_t* __restrict__ s
                     int d[4][4];
 #pragma unroll
                     for (int t = 0; t < 4; t++) mma_u8u8_16832(d[t], A.x, A.y, A.z, A.w, wl[t], wh[t]);
-                    *reinterpret_cast<uint2*>(orow + (16 * m) * 32) = make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0));
-                    *reinterpret_cast<uint2*>(orow + (16 * m + 8) * 32) = make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1));
+                    st_global_stream_v2(orow + (16 * m) * 32, make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0)));
+                    st_global_stream_v2(orow + (16 * m + 8) * 32, make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1)));
                 }
             } else {
                 // A = Hankel windows of the left reference (rows y = 16m + g, g + 8), B = W^T from the table
@@ -213,8 +213,8 @@ __device__ __forceinline__ void intra_generate(int mode, uint8_t* __restrict__ s
                     mma_u8u8_16832(d[1], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T0.z, T0.w);
                     mma_u8u8_16832(d[2], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T1.x, T1.y);
                     mma_u8u8_16832(d[3], win[2 * m], win[2 * m + 1], wpat[2 * m], wpat[2 * m + 1], T1.z, T1.w);
-                    *reinterpret_cast<uint2*>(orow + (16 * m) * 32) = make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0));
-                    *reinterpret_cast<uint2*>(orow + (16 * m + 8) * 32) = make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1));
+                    st_global_stream_v2(orow + (16 * m) * 32, make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0)));
+                    st_global_stream_v2(orow + (16 * m + 8) * 32, make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1)));
                 }
             }
             __syncwarp();
@@ -248,7 +248,7 @@ __device__ __forceinline__ void intra_generate(int mode, uint8_t* __restrict__ s
             // mode 2 (angle +32 on the left reference): P_v[r][c] = ref[c + r + 2] is symmetric, so P = P_v^T = P_v
 #pragma unroll
             for (int it = 0; it < 2; it++)
-                reinterpret_cast<uint4*>(out)[it * 32 + lane] = make_uint4(w[it][0], w[it][1], w[it][2], w[it][3]);
+                st_global_stream(reinterpret_cast<uint4*>(out) + it * 32 + lane, make_uint4(w[it][0], w[it][1], w[it][2], w[it][3]));
         } else {
 #pragma unroll
             for (int it = 0; it < 2; it++) {
@@ -310,8 +310,8 @@ __device__ __forceinline__ void intra_generate(int mode, uint8_t* __restrict__ s
             int d[4][4];
 #pragma unroll
             for (int t = 0; t < 4; t++) mma_u8u8_16832(d[t], Af[0], Af[1], 0u, 0u, Bf[t], 0u);
-            *reinterpret_cast<uint2*>(orow + (16 * m) * 32) = make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0));
-            *reinterpret_cast<uint2*>(orow + (16 * m + 8) * 32) = make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1));
+            st_global_stream_v2(orow + (16 * m) * 32, make_uint2(word(d[0], d[1], 0), word(d[2], d[3], 0)));
+            st_global_stream_v2(orow + (16 * m + 8) * 32, make_uint2(word(d[0], d[1], 1), word(d[2], d[3], 1)));
         }
     } else {
         __syncwarp();
